@@ -1,0 +1,404 @@
+// bf16 GEMM on tcgen05 tensor cores for sm_100a.
+//
+//   D[M,N] = epilogue(A[M,K] * B[N,K]^T), fp32 accumulation in TMEM.
+//
+// One persistent CTA per SM, 256 threads, warp-specialised:
+//   warp 0      TMA producer   (cp.async.bulk.tensor -> 128B-swizzled smem ring)
+//   warp 1      MMA issuer     (one lane issues tcgen05.mma, commits to mbarriers)
+//   warp 2      TMEM allocator
+//   warps 4..7  epilogue       (tcgen05.ld -> registers -> fused epilogue -> global)
+// Pipelines: smem full/empty ring (TMA <-> MMA) and a 2-deep TMEM accumulator
+// ring (MMA <-> epilogue) so the epilogue of tile i overlaps the MMAs of tile i+1.
+//
+// Tile: 128 x block_n x 64 (block_n in {64,128,256}, chosen at launch).  Both
+// operands may be K-major or MN-major (see mmdit_b200.h), which gives fprop,
+// dgrad and wgrad from the same kernel without transposed copies.  Split-K
+// (fp32 atomics) keeps all SMs busy on the small-output / long-reduction wgrads.
+#include "common.cuh"
+#include "mmdit_b200.h"
+
+namespace mmdit {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;
+constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KiB
+constexpr int MAX_STAGES = 8;
+constexpr int GEMM_THREADS = 256;
+constexpr int SMEM_BUDGET = 227 * 1024;
+constexpr int BAR_BYTES = 256;
+
+struct GemmParams {
+  CUtensorMap tmA, tmB;
+  int M, N, K;
+  int block_n, stages;
+  int a_mn, b_mn;
+  int tiles_m, tiles_n, split_k, kb_total, kb_per_split;
+  // epilogue
+  void* D;
+  long long ldd;
+  int d_fp32, accumulate, epi;
+  const void* bias;
+  int bias_fp32;
+  const bf16* gate;
+  long long rows_per_gate, ld_gate;
+  const bf16* resid;
+  long long ldr;
+  bf16* aux;
+  long long ld_aux;
+  long long remap_rows, remap_batch_rows, remap_offset;
+};
+
+__device__ __forceinline__ float bias_at(const GemmParams& p, int n) {
+  if (!p.bias) return 0.f;
+  return p.bias_fp32 ? reinterpret_cast<const float*>(p.bias)[n]
+                     : __bfloat162float(reinterpret_cast<const bf16*>(p.bias)[n]);
+}
+
+// Fused epilogue for 8 consecutive columns [n, n+8) of output row m (physical row drow).
+__device__ __forceinline__ void epilogue8(const GemmParams& p, long long m, long long drow, int n,
+                                          float (&v)[8], int nvalid) {
+  if (p.bias) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (j < nvalid) v[j] += bias_at(p, n + j);
+  }
+  const bool full = (nvalid == 8);
+  if (p.aux) {
+    bf16* ap = p.aux + drow * p.ld_aux + n;
+    if (full && ((reinterpret_cast<uintptr_t>(ap) & 15) == 0)) {
+      store8(ap, v);
+    } else {
+      for (int j = 0; j < nvalid; ++j) ap[j] = __float2bfloat16(v[j]);
+    }
+  }
+  if (p.epi == MMDIT_EPI_GATE_RESID || p.epi == MMDIT_EPI_RESID) {
+    float g[8], r[8];
+    if (p.epi == MMDIT_EPI_GATE_RESID) {
+      const bf16* gp = p.gate + (m / p.rows_per_gate) * p.ld_gate + n;
+      if (full && ((reinterpret_cast<uintptr_t>(gp) & 15) == 0)) {
+        load8(gp, g);
+      } else {
+        for (int j = 0; j < 8; ++j) g[j] = j < nvalid ? __bfloat162float(gp[j]) : 0.f;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) g[j] = 1.f;
+    }
+    const bf16* rp = p.resid + drow * p.ldr + n;
+    if (full && ((reinterpret_cast<uintptr_t>(rp) & 15) == 0)) {
+      load8(rp, r);
+    } else {
+      for (int j = 0; j < 8; ++j) r[j] = j < nvalid ? __bfloat162float(rp[j]) : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], g[j], r[j]);
+  } else if (p.epi == MMDIT_EPI_SILU) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = silu_f(v[j]);
+  }
+  if (!p.d_fp32) {
+    bf16* dp = reinterpret_cast<bf16*>(p.D) + drow * p.ldd + n;
+    if (full && ((reinterpret_cast<uintptr_t>(dp) & 15) == 0)) {
+      store8(dp, v);
+    } else {
+      for (int j = 0; j < nvalid; ++j) dp[j] = __float2bfloat16(v[j]);
+    }
+  } else {
+    float* dp = reinterpret_cast<float*>(p.D) + drow * p.ldd + n;
+    if (p.accumulate) {
+      if (p.split_k > 1) {
+        for (int j = 0; j < nvalid; ++j) atomicAdd(dp + j, v[j]);
+      } else if (full && ((reinterpret_cast<uintptr_t>(dp) & 15) == 0)) {
+        float4 a = *reinterpret_cast<float4*>(dp), b = *reinterpret_cast<float4*>(dp + 4);
+        a.x += v[0]; a.y += v[1]; a.z += v[2]; a.w += v[3];
+        b.x += v[4]; b.y += v[5]; b.z += v[6]; b.w += v[7];
+        *reinterpret_cast<float4*>(dp) = a;
+        *reinterpret_cast<float4*>(dp + 4) = b;
+      } else {
+        for (int j = 0; j < nvalid; ++j) dp[j] += v[j];
+      }
+    } else if (full && ((reinterpret_cast<uintptr_t>(dp) & 15) == 0)) {
+      *reinterpret_cast<float4*>(dp) = make_float4(v[0], v[1], v[2], v[3]);
+      *reinterpret_cast<float4*>(dp + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    } else {
+      for (int j = 0; j < nvalid; ++j) dp[j] = v[j];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  // 128B-swizzled tiles need 1024 B alignment in the shared window.
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int block_n = p.block_n;
+  const int b_stage_bytes = block_n * BLOCK_K * 2;
+  const int stage_bytes = A_STAGE_BYTES + b_stage_bytes;
+  const int stages = p.stages;
+
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + stages * stage_bytes);
+  uint64_t* empty_bar = full_bar + MAX_STAGES;
+  uint64_t* tmem_full = empty_bar + MAX_STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const uint32_t tmem_cols = 2u * block_n;  // 128 / 256 / 512: powers of two
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmA);
+    tma_prefetch_desc(&p.tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full[s], 1);
+      mbar_init(&tmem_empty[s], 4);  // one arrive per epilogue warp
+    }
+    mbar_fence_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int total_work = p.tiles_m * p.tiles_n * p.split_k;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int work = blockIdx.x; work < total_work; work += gridDim.x) {
+        const int tile = work / p.split_k, ks = work % p.split_k;
+        const int m_blk = tile % p.tiles_m, n_blk = tile / p.tiles_m;
+        const int kb0 = ks * p.kb_per_split;
+        const int kb1 = min(kb0 + p.kb_per_split, p.kb_total);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sA = smem + stage * stage_bytes;
+          uint8_t* sB = sA + A_STAGE_BYTES;
+          mbar_expect_tx(&full_bar[stage], stage_bytes);
+          if (!p.a_mn) {
+            tma_load_2d(sA, &p.tmA, &full_bar[stage], kb * BLOCK_K, m_blk * BLOCK_M);
+          } else {
+            for (int i = 0; i < BLOCK_M / 64; ++i)
+              tma_load_2d(sA + i * (BLOCK_K * 128), &p.tmA, &full_bar[stage],
+                          m_blk * BLOCK_M + i * 64, kb * BLOCK_K);
+          }
+          if (!p.b_mn) {
+            tma_load_2d(sB, &p.tmB, &full_bar[stage], kb * BLOCK_K, n_blk * block_n);
+          } else {
+            for (int i = 0; i < block_n / 64; ++i)
+              tma_load_2d(sB + i * (BLOCK_K * 128), &p.tmB, &full_bar[stage],
+                          n_blk * block_n + i * 64, kb * BLOCK_K);
+          }
+          if (++stage == stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // -------------------------------------------------------------- MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(BLOCK_M, block_n, p.a_mn, p.b_mn);
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      for (int work = blockIdx.x; work < total_work; work += gridDim.x) {
+        const int ks = work % p.split_k;
+        const int kb0 = ks * p.kb_per_split;
+        const int kb1 = min(kb0 + p.kb_per_split, p.kb_total);
+        mbar_wait(&tmem_empty[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * block_n;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + stage * stage_bytes);
+          const uint32_t b_addr = a_addr + A_STAGE_BYTES;
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / 16; ++k) {
+            const uint64_t adesc =
+                p.a_mn ? desc_mnmajor(a_addr, k, BLOCK_K * 128) : desc_kmajor(a_addr, k);
+            const uint64_t bdesc =
+                p.b_mn ? desc_mnmajor(b_addr, k, BLOCK_K * 128) : desc_kmajor(b_addr, k);
+            umma_bf16(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+          if (++stage == stages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tmem_full[as]);  // accumulator ready for the epilogue
+        as ^= 1;
+        if (as == 0) aphase ^= 1;
+      }
+    }
+  } else if (warp >= 4) {
+    // ---------------------------------------------------------------- epilogue
+    const int ew = warp - 4;  // == warp % 4 -> TMEM lane quarter
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int work = blockIdx.x; work < total_work; work += gridDim.x) {
+      const int tile = work / p.split_k;
+      const int m_blk = tile % p.tiles_m, n_blk = tile / p.tiles_m;
+      mbar_wait(&tmem_full[as], aphase);
+      tc_fence_after();
+      const long long m = static_cast<long long>(m_blk) * BLOCK_M + ew * 32 + lane;
+      long long drow = m;
+      if (p.remap_rows > 0)
+        drow = (m / p.remap_rows) * p.remap_batch_rows + (m % p.remap_rows) + p.remap_offset;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + as * block_n;
+      for (int c = 0; c < block_n / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld32(taddr + c * 32, r);
+        tmem_ld_wait();
+        const int n0 = n_blk * block_n + c * 32;
+        if (m < p.M && n0 < p.N) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int n = n0 + g * 8;
+            const int nvalid = min(8, p.N - n);
+            if (nvalid > 0) {
+              float v[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g * 8 + j]);
+              epilogue8(p, m, drow, n, v, nvalid);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[as]);
+      as ^= 1;
+      if (as == 0) aphase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, tmem_cols);
+}
+
+static int pick_block_n(long long M, long long N, int sms) {
+  if (N <= 64) return 64;
+  if (N <= 128) return 128;
+  // prefer 256 unless it leaves the machine visibly under-filled
+  const long long tm = (M + BLOCK_M - 1) / BLOCK_M;
+  const long long t256 = tm * ((N + 255) / 256);
+  const long long t128 = tm * ((N + 127) / 128);
+  auto eff = [&](long long t, double cost) {
+    long long waves = (t + sms - 1) / sms;
+    return (double)t / (double)(waves * sms) / cost;
+  };
+  // 128-wide tiles run the MMA pipe at the same rate but double A traffic; small penalty
+  return eff(t256, 1.0) >= eff(t128, 1.08) ? 256 : 128;
+}
+
+}  // namespace mmdit
+
+using namespace mmdit;
+
+extern "C" int mmdit_gemm_bf16(const mmdit_gemm_args* a, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  MMDIT_REQUIRE(a && a->A && a->B && a->D, MMDIT_ERR_ARG, "gemm: null pointer argument");
+  MMDIT_REQUIRE(a->M > 0 && a->N > 0 && a->K > 0, MMDIT_ERR_ARG, "gemm: bad shape %lld %lld %lld",
+                (long long)a->M, (long long)a->N, (long long)a->K);
+  MMDIT_REQUIRE(a->M < (1ll << 31) && a->N < (1ll << 31) && a->K < (1ll << 31), MMDIT_ERR_ARG,
+                "gemm: dimension exceeds int32");
+  MMDIT_REQUIRE(a->lda % 8 == 0 && a->ldb % 8 == 0, MMDIT_ERR_ALIGN,
+                "gemm: lda/ldb must be multiples of 8 elements (16 B) for TMA, got %lld %lld",
+                (long long)a->lda, (long long)a->ldb);
+  MMDIT_REQUIRE(!(a->accumulate && !a->d_fp32), MMDIT_ERR_ARG, "gemm: accumulate needs fp32 D");
+  MMDIT_REQUIRE(a->epilogue == MMDIT_EPI_NONE || a->epilogue == MMDIT_EPI_GATE_RESID ||
+                    a->epilogue == MMDIT_EPI_SILU || a->epilogue == MMDIT_EPI_RESID,
+                MMDIT_ERR_UNSUPPORTED, "gemm: epilogue %d not supported", a->epilogue);
+  if (a->epilogue == MMDIT_EPI_GATE_RESID)
+    MMDIT_REQUIRE(a->gate && a->rows_per_gate > 0 && a->resid, MMDIT_ERR_ARG,
+                  "gemm: gate/resid epilogue needs gate, rows_per_gate, resid");
+  if (a->epilogue == MMDIT_EPI_RESID)
+    MMDIT_REQUIRE(a->resid != nullptr, MMDIT_ERR_ARG, "gemm: resid epilogue needs resid");
+
+  const int sms = num_sms();
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = (int)a->M; p.N = (int)a->N; p.K = (int)a->K;
+  p.a_mn = a->a_major ? 1 : 0;
+  p.b_mn = a->b_major ? 1 : 0;
+  p.block_n = a->force_block_n ? a->force_block_n : pick_block_n(a->M, a->N, sms);
+  MMDIT_REQUIRE(p.block_n == 64 || p.block_n == 128 || p.block_n == 256, MMDIT_ERR_ARG,
+                "gemm: block_n %d", p.block_n);
+  const int stage_bytes = A_STAGE_BYTES + p.block_n * BLOCK_K * 2;
+  p.stages = (SMEM_BUDGET - 1024 - BAR_BYTES) / stage_bytes;
+  if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
+  p.tiles_m = (p.M + BLOCK_M - 1) / BLOCK_M;
+  p.tiles_n = (p.N + p.block_n - 1) / p.block_n;
+  p.kb_total = (p.K + BLOCK_K - 1) / BLOCK_K;
+  int split = a->split_k;
+  const int tiles = p.tiles_m * p.tiles_n;
+  if (split <= 0) {
+    split = 1;
+    if (a->accumulate && tiles < sms && p.kb_total >= 8) {
+      split = (sms + tiles - 1) / tiles;
+      if (split > p.kb_total / 4) split = p.kb_total / 4;
+      if (split < 1) split = 1;
+    }
+  }
+  MMDIT_REQUIRE(split == 1 || (a->accumulate && a->d_fp32), MMDIT_ERR_ARG,
+                "gemm: split_k > 1 needs fp32 accumulate output");
+  if (split > p.kb_total) split = p.kb_total;
+  p.kb_per_split = (p.kb_total + split - 1) / split;
+  p.split_k = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
+
+  p.D = a->D; p.ldd = a->ldd; p.d_fp32 = a->d_fp32; p.accumulate = a->accumulate;
+  p.epi = a->epilogue;
+  p.bias = a->bias; p.bias_fp32 = a->bias_fp32;
+  p.gate = static_cast<const bf16*>(a->gate);
+  p.rows_per_gate = a->rows_per_gate; p.ld_gate = a->ld_gate;
+  p.resid = static_cast<const bf16*>(a->resid); p.ldr = a->ldr;
+  p.aux = static_cast<bf16*>(a->aux); p.ld_aux = a->ld_aux;
+  p.remap_rows = a->remap_rows; p.remap_batch_rows = a->remap_batch_rows;
+  p.remap_offset = a->remap_offset;
+
+  // Tensor maps. dims are innermost-first.
+  {
+    uint64_t dims[2], strides[1];
+    uint32_t box[2];
+    if (!p.a_mn) { dims[0] = a->K; dims[1] = a->M; box[0] = BLOCK_K; box[1] = BLOCK_M; }
+    else         { dims[0] = a->M; dims[1] = a->K; box[0] = 64;      box[1] = BLOCK_K; }
+    strides[0] = (uint64_t)a->lda * 2;
+    int rc = encode_tmap(&p.tmA, a->A, 2, dims, strides, box, 2, true);
+    if (rc) return rc;
+    if (!p.b_mn) { dims[0] = a->K; dims[1] = a->N; box[0] = BLOCK_K; box[1] = (uint32_t)p.block_n; }
+    else         { dims[0] = a->N; dims[1] = a->K; box[0] = 64;      box[1] = BLOCK_K; }
+    strides[0] = (uint64_t)a->ldb * 2;
+    rc = encode_tmap(&p.tmB, a->B, 2, dims, strides, box, 2, true);
+    if (rc) return rc;
+  }
+
+  const int smem_bytes = p.stages * stage_bytes + BAR_BYTES + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET);
+    if (e != cudaSuccess) {
+      set_last_error("gemm: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return (int)e;
+    }
+    attr_set = true;
+  }
+  const int total_work = tiles * p.split_k;
+  const int grid = total_work < sms ? total_work : sms;
+  gemm_tcgen05_kernel<<<grid, GEMM_THREADS, smem_bytes, stream>>>(p);
+  return check_launch("gemm_tcgen05_kernel");
+}

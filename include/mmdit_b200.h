@@ -86,6 +86,118 @@ int mmdit_gemm_bf16(const mmdit_gemm_args* args, void* stream);
  * tests to cross-check the tcgen05 path on the device; never on the product path. */
 int mmdit_gemm_bf16_simt(const mmdit_gemm_args* args, void* stream);
 
+
+/* ------------------------------------------------------------- attention --
+ * Joint text+image softmax attention, head_dim 64, non-causal, fp32 softmax.
+ * Replaces flash_attn_func and the concat/transpose/split copies around it
+ * (Attention.py:259-263, 293, 411-417) and their autograd.
+ * Streams: [0] = image tokens (N per sample), [1] = text tokens (M per sample);
+ * the joint sequence order is image first, then text (Attention.py:259-261).
+ * Every operand is a [B*rows, ld] bf16 matrix in which head h occupies columns
+ * [h*64, h*64+64) from the given base pointer, so q/k/v may live inside packed
+ * QKV buffers.  lse / delta: fp32 [B, H, N+M]; dq_acc: fp32 [B, N+M, H*64].
+ */
+typedef struct mmdit_attn_args {
+  const void* q[2]; const void* k[2]; const void* v[2];
+  int64_t ld_q[2], ld_k[2], ld_v[2];
+  void* o[2];            /* fwd: output; bwd: forward output (input) */
+  int64_t ld_o[2];
+  float* lse;            /* fwd: output; bwd: input */
+  int32_t B, H, N, M, head_dim;
+  float scale;
+  /* backward only */
+  const void* d_o[2]; int64_t ld_do[2];
+  void* dq[2]; void* dk[2]; void* dv[2];
+  int64_t ld_dq[2], ld_dk[2], ld_dv[2];
+  float* delta;          /* workspace */
+  float* dq_acc;         /* workspace */
+} mmdit_attn_args;
+
+int mmdit_attn_fwd(const mmdit_attn_args* args, void* stream);
+int mmdit_attn_bwd(const mmdit_attn_args* args, void* stream);
+
+/* ------------------------------------------------- adaLN LayerNorm-modulate --
+ * y = LN(x) * (1 + scale[b]) + shift[b], LN eps, no affine (Norm.py:16-23).
+ * shift/scale: bf16 [B, d] with row stride ld_mod; b = row / rows_per_batch.
+ * bwd: dx = LN-backward(dy * (1+scale)) (+ dres), dshift/dscale (fp32, row
+ * stride ld_dmod) are ACCUMULATED with atomics -- zero them first. */
+int mmdit_ln_modulate_fwd(const void* x, const void* shift, const void* scale, void* y, float* mean,
+                          float* rstd, int64_t rows, int32_t d, int64_t rows_per_batch,
+                          int64_t ld_mod, float eps, void* stream);
+int mmdit_ln_modulate_bwd(const void* dy, const void* x, const float* mean, const float* rstd,
+                          const void* scale, const void* dres, void* dx, float* dshift,
+                          float* dscale, int64_t rows, int32_t d, int64_t rows_per_batch,
+                          int64_t ld_mod, int64_t ld_dmod, void* stream);
+
+/* Backward of the gated residual o = a * gate[b] + x (Transformer_Block_Dual.py:64-76):
+ * da = dout * gate[b]; dgate[b] += sum_rows dout * a; dab[b] += sum_rows da (optional,
+ * per-sample partial of the bias gradient of the producing linear). fp32 outputs accumulate. */
+int mmdit_gate_bwd(const void* dout, const void* a, const void* gate, void* da, float* dgate,
+                   float* dab, int64_t rows, int32_t d, int64_t rows_per_batch, int64_t ld_gate,
+                   int64_t ld_dgate, int64_t ld_dab, void* stream);
+
+/* Text front-end (diff_model.py:168-172,323-326): out = bf16(sigma * RMSNorm_fp32(c) * w).
+ * Tokens [0,split) of each sample use (w1,sigma1) -> out1 [B*split, d]; tokens [split,M)
+ * use (w2,sigma2) -> out2 [B*(M-split), d]. rstd: fp32 [B*M] saved for backward. */
+int mmdit_text_norm_fwd(const void* c, const float* w1, const float* w2, const float* sigma1,
+                        const float* sigma2, void* out1, void* out2, float* rstd, int64_t batch,
+                        int32_t tokens, int32_t split, int32_t d, float eps, void* stream);
+/* One half: dn = grad wrt out half [B*ntok, d]; accumulates dw [d] and dsigma [1]. */
+int mmdit_text_norm_bwd(const void* dn, const void* c, const float* rstd, const float* w,
+                        const float* sigma, float* dw, float* dsigma, int64_t batch, int32_t tokens,
+                        int32_t tok0, int32_t ntok, int32_t d, void* stream);
+
+/* Per-head QK RMSNorm (+ 2-D axial RoPE on image tokens) (Attention.py:61-64,130-134,
+ * 174-194; rotary_embedding.py:36-76,269-288).  qkv: raw projections, q at column 0 and
+ * k at column d of each row (stride ld_in).  out: q at 0, k at d (stride ld_out).
+ * rope_cos/rope_sin: fp32 [tokens_per_sample, 32] or NULL (text stream). */
+int mmdit_qknorm_rope_fwd(const void* qkv, const float* wq, const float* wk, const float* rope_cos,
+                          const float* rope_sin, void* out, int64_t rows, int32_t d, int64_t ld_in,
+                          int64_t ld_out, int32_t tokens_per_sample, float eps, void* stream);
+int mmdit_qknorm_rope_bwd(const void* dqk, const void* qkv, const float* wq, const float* wk,
+                          const float* rope_cos, const float* rope_sin, void* dqkv, float* dwq,
+                          float* dwk, int64_t rows, int32_t d, int64_t ld_g, int64_t ld_in,
+                          int64_t ld_dout, int32_t tokens_per_sample, float eps, void* stream);
+
+/* SwiGLU activation, xformers semantics (MLP.py:19,32): h12 = [x1 | x2], a = silu(x1) * x2.
+ * bwd writes dh12 and accumulates db12 [2*hidden] (may be NULL). */
+int mmdit_swiglu_fwd(const void* h12, void* a, int64_t rows, int32_t hidden, void* stream);
+int mmdit_swiglu_bwd(const void* da, const void* h12, void* dh12, float* db12, int64_t rows,
+                     int32_t hidden, void* stream);
+
+/* Timestep embedding (PositionalEncoding.py:23-30 with t * time_scale, diff_model.py:306):
+ * out bf16 [B, d]; denom fp32 [d] as built by the reference ctor. bwd accumulates dscale[1]. */
+int mmdit_timestep_embed_fwd(const float* t, const float* time_scale, const float* denom, void* out,
+                             int32_t batch, int32_t d, void* stream);
+int mmdit_timestep_embed_bwd(const void* de, const float* t, const float* time_scale,
+                             const float* denom, float* dscale, int32_t batch, int32_t d,
+                             void* stream);
+
+/* [B,C,H,W] <-> tokens [B*(H/p)*(W/p), C*p*p] bf16, column c*p*p + i*p + j
+ * (ImagePositionalEncoding.py:114-116,181-183 conv-as-GEMM input; patchify.py:41-72). */
+int mmdit_patchify(const void* img, int32_t img_fp32, void* tokens, int32_t B, int32_t C, int32_t H,
+                   int32_t W, int32_t p, void* stream);
+int mmdit_unpatchify(const void* tokens, void* img, int32_t img_fp32, int32_t B, int32_t C,
+                     int32_t H, int32_t W, int32_t p, void* stream);
+
+/* Rectified flow: x_t = (1-t) x0 + t eps (diff_model.py:229-241); loss = mean((v-(eps-x0))^2)
+ * with diff kept for backward (model_trainer.py:429-446); dv = upstream * 2/numel * diff;
+ * x -= ((1+w) v[:B] - w v[B:]) * dt (diff_model.py:419-429). */
+int mmdit_rf_noise(const void* x0, const void* eps, int32_t in_fp32, const float* t, float* xt,
+                   int64_t batch, int64_t per_sample, void* stream);
+int mmdit_rf_loss_fwd(const void* v, int32_t v_fp32, const void* eps, const void* x0,
+                      int32_t in_fp32, float* diff, float* loss, int64_t numel, void* stream);
+int mmdit_rf_loss_bwd(const float* diff, const float* upstream, void* dv, int32_t dv_fp32,
+                      int64_t numel, void* stream);
+int mmdit_cfg_euler_step(float* x, const void* v, int32_t v_fp32, int64_t half_numel,
+                         float cfg_scale, float dt, void* stream);
+
+/* out[n] += sum_rows in[row, n] (bias gradients); fold of per-sample fp32 partials; cast. */
+int mmdit_colsum_bf16(const void* in, float* out, int64_t rows, int32_t n, int64_t ld, void* stream);
+int mmdit_fold_rows_f32(const float* in, float* out, int32_t rows, int32_t n, int64_t ld,
+                        void* stream);
+int mmdit_cast_f32_bf16(const float* in, void* out, int64_t n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

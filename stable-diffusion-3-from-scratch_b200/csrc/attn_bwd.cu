@@ -1,0 +1,391 @@
+// Joint text+image softmax attention, backward, on tcgen05 tensor cores
+// (the autograd of flash_attn_func at Attention.py:293; math in SURVEY App. E).
+//
+// One CTA = one (sample, head, 128-key tile); it loops over all query tiles.
+// Everything is computed transposed so that each compute thread owns a key row:
+//   S^T  = K Q^T            dP^T = V dO^T                 (TMEM, 128 cols each)
+//   P^T  = exp2(S^T*c - LSE),   dS^T = P^T (dP^T - delta) * scale   -> bf16 smem
+//   dV  += P^T dO           dK  += dS^T Q                 (TMEM, 64 cols each)
+//   dQ_i = dS K   (A operand = dS^T read MN-major)        (TMEM, 64 cols)
+// dQ tiles are added into an fp32 accumulator with 128-bit vector reductions
+// (red.global.add.v4.f32); a small kernel converts it to bf16 afterwards.
+//   warp 0      TMA producer (K,V once; Q_i,dO_i through a 2-deep ring)
+//   warp 1      MMA issuer
+//   warps 2..9  compute: thread = (key row, 64-query half)
+#include "common.cuh"
+#include "mmdit_b200.h"
+
+namespace mmdit {
+
+constexpr int ATT_TILE = 128;
+constexpr int ATT_HD = 64;
+constexpr int ATT_TILE_BYTES = ATT_TILE * ATT_HD * 2;  // 16 KiB
+constexpr int BWD_THREADS = 320;
+constexpr int BWD_SMEM = 10 * ATT_TILE_BYTES + 2 * 2 * 128 * 4 + 256;
+
+int make_attn_tmap(CUtensorMap* map, const void* base, long long ld, int H, int rows, int B);
+
+struct AttnBwdParams {
+  CUtensorMap tmQ[2], tmK[2], tmV[2], tmdO[2];
+  bf16* dk[2];
+  bf16* dv[2];
+  long long ld_dk[2], ld_dv[2];
+  const float* lse;    // [B,H,T]
+  const float* delta;  // [B,H,T]
+  float* dq_acc;       // [B, T, H*64] fp32
+  int B, H, N, M;
+  float scale, scale_log2;
+};
+
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c),
+               "f"(d)
+               : "memory");
+}
+
+__global__ void __launch_bounds__(BWD_THREADS, 1)
+attn_bwd_kernel(const __grid_constant__ AttnBwdParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sK = smem;
+  uint8_t* sV = smem + ATT_TILE_BYTES;
+  uint8_t* sQ = smem + 2 * ATT_TILE_BYTES;    // [2]
+  uint8_t* sdO = smem + 4 * ATT_TILE_BYTES;   // [2]
+  uint8_t* sPt = smem + 6 * ATT_TILE_BYTES;   // 2 halves
+  uint8_t* sdSt = smem + 8 * ATT_TILE_BYTES;  // 2 halves
+  float* sLse = reinterpret_cast<float*>(smem + 10 * ATT_TILE_BYTES);  // [2][128]
+  float* sDelta = sLse + 256;                                          // [2][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sDelta + 256);
+  uint64_t* kv_full = bars + 0;
+  uint64_t* qdo_full = bars + 1;   // [2]
+  uint64_t* qdo_empty = bars + 3;  // [2]
+  uint64_t* st_full = bars + 5;
+  uint64_t* pt_full = bars + 6;
+  uint64_t* dq_full = bars + 7;
+  uint64_t* dq_empty = bars + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int T = p.N + p.M;
+  const int ntx = (p.N + ATT_TILE - 1) / ATT_TILE;
+  const int ntc = (p.M + ATT_TILE - 1) / ATT_TILE;
+  const int nt = ntx + ntc;
+  const int kt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int ks = kt < ntx ? 0 : 1;
+  const int k_row0 = (ks == 0 ? kt : kt - ntx) * ATT_TILE;
+  const int k_rows = ks == 0 ? p.N : p.M;
+  const int k_valid = min(ATT_TILE, k_rows - k_row0);
+
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  if (warp == 1 && lane == 0) {
+    mbar_init(kv_full, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(&qdo_full[s], 1); mbar_init(&qdo_empty[s], 1); }
+    mbar_init(st_full, 1);
+    mbar_init(pt_full, 256);
+    mbar_init(dq_full, 1);
+    mbar_init(dq_empty, 256);
+    mbar_fence_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tm_St = tmem_base, tm_dPt = tmem_base + 128, tm_dV = tmem_base + 256,
+                 tm_dK = tmem_base + 320, tm_dQ = tmem_base + 384;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(kv_full, 2 * ATT_TILE_BYTES);
+      tma_load_4d(sK, &p.tmK[ks], kv_full, 0, h, k_row0, b);
+      tma_load_4d(sV, &p.tmV[ks], kv_full, 0, h, k_row0, b);
+      for (int i = 0; i < nt; ++i) {
+        const int st = i & 1;
+        const int qs = i < ntx ? 0 : 1;
+        const int row0 = (qs == 0 ? i : i - ntx) * ATT_TILE;
+        mbar_wait(&qdo_empty[st], ((i >> 1) & 1) ^ 1);
+        mbar_expect_tx(&qdo_full[st], 2 * ATT_TILE_BYTES);
+        tma_load_4d(sQ + st * ATT_TILE_BYTES, &p.tmQ[qs], &qdo_full[st], 0, h, row0, b);
+        tma_load_4d(sdO + st * ATT_TILE_BYTES, &p.tmdO[qs], &qdo_full[st], 0, h, row0, b);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t id_kk = make_idesc_bf16(128, 128, 0, 0);  // S^T, dP^T
+      const uint32_t id_kn = make_idesc_bf16(128, 64, 0, 1);   // dV, dK
+      const uint32_t id_nn = make_idesc_bf16(128, 64, 1, 1);   // dQ
+      const uint32_t k_addr = smem_u32(sK), v_addr = smem_u32(sV);
+      const uint32_t pt_addr = smem_u32(sPt), dst_addr = smem_u32(sdSt);
+      mbar_wait(kv_full, 0);
+      for (int i = 0; i < nt; ++i) {
+        const int st = i & 1;
+        const uint32_t q_addr = smem_u32(sQ + st * ATT_TILE_BYTES);
+        const uint32_t do_addr = smem_u32(sdO + st * ATT_TILE_BYTES);
+        mbar_wait(&qdo_full[st], (i >> 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(tm_St, desc_kmajor(k_addr, k), desc_kmajor(q_addr, k), id_kk, k > 0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(tm_dPt, desc_kmajor(v_addr, k), desc_kmajor(do_addr, k), id_kk, k > 0);
+        umma_commit(st_full);
+        mbar_wait(pt_full, i & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          umma_bf16(tm_dV, desc_kmajor(pt_addr + (k >> 2) * ATT_TILE_BYTES, k & 3),
+                    desc_mnmajor(do_addr, k, ATT_TILE_BYTES), id_kn, (i > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          umma_bf16(tm_dK, desc_kmajor(dst_addr + (k >> 2) * ATT_TILE_BYTES, k & 3),
+                    desc_mnmajor(q_addr, k, ATT_TILE_BYTES), id_kn, (i > 0 || k > 0) ? 1u : 0u);
+        if (i > 0) {
+          mbar_wait(dq_empty, (i - 1) & 1);
+          tc_fence_after();
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          umma_bf16(tm_dQ, desc_mnmajor(dst_addr, k, ATT_TILE_BYTES),
+                    desc_mnmajor(k_addr, k, ATT_TILE_BYTES), id_nn, k > 0);
+        umma_commit(&qdo_empty[st]);
+        umma_commit(dq_full);
+      }
+    }
+  } else {
+    // ---------------------------------------------------------------- compute
+    const int cw = warp - 2;
+    const int quarter = warp & 3;
+    const int hf = cw >> 2;             // which 64-wide half of the query tile
+    const int r = quarter * 32 + lane;  // key row in the tile == TMEM lane
+    const int ct = cw * 32 + lane;      // 0..255
+    const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
+    const bool k_ok = r < k_valid;
+    const float sl2 = p.scale_log2;
+    const long long lse_base = ((long long)b * p.H + h) * T;
+    for (int i = 0; i < nt; ++i) {
+      const int qs = i < ntx ? 0 : 1;
+      const int row0 = (qs == 0 ? i : i - ntx) * ATT_TILE;
+      const int q_valid = min(ATT_TILE, (qs == 0 ? p.N : p.M) - row0);
+      const int t0 = (qs == 0 ? 0 : p.N) + row0;
+      float* lse_s = sLse + (i & 1) * 128;
+      float* del_s = sDelta + (i & 1) * 128;
+      if (ct < 128) {
+        const bool ok = ct < q_valid;
+        lse_s[ct] = ok ? p.lse[lse_base + t0 + ct] * 1.4426950408889634f : INFINITY;
+        del_s[ct] = ok ? p.delta[lse_base + t0 + ct] : 0.f;
+      }
+      named_bar_sync(1, 256);
+      mbar_wait(st_full, i & 1);
+      tc_fence_after();
+      if (i > 0) mbar_wait(dq_full, (i - 1) & 1);  // MMAs of tile i-1 no longer read sPt/sdSt
+#pragma unroll 1
+      for (int c = 0; c < 2; ++c) {
+        uint32_t s[32], dp[32];
+        tmem_ld32(tm_St + lane_off + hf * 64 + c * 32, s);
+        tmem_ld32(tm_dPt + lane_off + hf * 64 + c * 32, dp);
+        tmem_ld_wait();
+        uint8_t* prow = sPt + hf * ATT_TILE_BYTES + r * 128;
+        uint8_t* drow = sdSt + hf * ATT_TILE_BYTES + r * 128;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          float pe[8], de[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int col = hf * 64 + c * 32 + g * 8 + j;
+            const float pv =
+                k_ok ? exp2f(fmaf(__uint_as_float(s[g * 8 + j]), sl2, -lse_s[col])) : 0.f;
+            pe[j] = pv;
+            de[j] = pv * (__uint_as_float(dp[g * 8 + j]) - del_s[col]) * p.scale;
+          }
+          uint4 u, w;
+          u.x = pack_bf16x2(pe[0], pe[1]); u.y = pack_bf16x2(pe[2], pe[3]);
+          u.z = pack_bf16x2(pe[4], pe[5]); u.w = pack_bf16x2(pe[6], pe[7]);
+          w.x = pack_bf16x2(de[0], de[1]); w.y = pack_bf16x2(de[2], de[3]);
+          w.z = pack_bf16x2(de[4], de[5]); w.w = pack_bf16x2(de[6], de[7]);
+          const int off = ((c * 4 + g) ^ (r & 7)) << 4;
+          *reinterpret_cast<uint4*>(prow + off) = u;
+          *reinterpret_cast<uint4*>(drow + off) = w;
+        }
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(pt_full);
+      // drain dQ_i: thread = (query row r, 32-column chunk hf)
+      mbar_wait(dq_full, i & 1);
+      tc_fence_after();
+      {
+        uint32_t q[32];
+        tmem_ld32(tm_dQ + lane_off + hf * 32, q);
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(dq_empty);
+        if (r < q_valid) {
+          float* dst = p.dq_acc + ((long long)b * T + t0 + r) * (p.H * ATT_HD) + h * ATT_HD + hf * 32;
+#pragma unroll
+          for (int g = 0; g < 8; ++g)
+            red_add_v4(dst + g * 4, __uint_as_float(q[g * 4]), __uint_as_float(q[g * 4 + 1]),
+                       __uint_as_float(q[g * 4 + 2]), __uint_as_float(q[g * 4 + 3]));
+        }
+      }
+    }
+    // dq_full(nt-1) was awaited above: all MMAs (incl. the last dV/dK updates) have retired.
+    {
+      uint32_t a[32], c2[32];
+      tmem_ld32(tm_dV + lane_off + hf * 32, a);
+      tmem_ld32(tm_dK + lane_off + hf * 32, c2);
+      tmem_ld_wait();
+      if (k_ok) {
+        const long long grow = (long long)b * k_rows + k_row0 + r;
+        bf16* dvp = p.dv[ks] + grow * p.ld_dv[ks] + h * ATT_HD + hf * 32;
+        bf16* dkp = p.dk[ks] + grow * p.ld_dk[ks] + h * ATT_HD + hf * 32;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          float v[8], w[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            v[j] = __uint_as_float(a[g * 8 + j]);
+            w[j] = __uint_as_float(c2[g * 8 + j]);
+          }
+          store8(dvp + g * 8, v);
+          store8(dkp + g * 8, w);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 512);
+}
+
+// delta[b,h,t] = sum_e dO[b,t,h,e] * O[b,t,h,e]; 8 lanes per (row, head).
+__global__ void __launch_bounds__(256)
+attn_delta_kernel(const bf16* __restrict__ o, const bf16* __restrict__ d_o, float* __restrict__ delta,
+                  long long rows, int H, long long ld_o, long long ld_do, int rows_per_sample,
+                  int t_off, int T) {
+  const long long total = rows * H * 8;
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const bool active = idx < total;
+  const long long rh = active ? idx / 8 : 0;
+  const int part = (int)(idx & 7);
+  const long long row = rh / H;
+  const int h = (int)(rh % H);
+  float a[8], g[8];
+  float acc = 0.f;
+  if (active) {
+    load8(o + row * ld_o + h * 64 + part * 8, a);
+    load8(d_o + row * ld_do + h * 64 + part * 8, g);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc += a[j] * g[j];
+  }
+#pragma unroll
+  for (int off = 1; off < 8; off <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+  if (active && part == 0) {
+    const long long bb = row / rows_per_sample;
+    const int t = t_off + (int)(row % rows_per_sample);
+    delta[(bb * H + h) * T + t] = acc;
+  }
+}
+
+// dq (bf16, stream layout) = dq_acc (fp32 [B,T,H*64]) rows of one stream
+__global__ void __launch_bounds__(256)
+attn_dq_convert_kernel(const float* __restrict__ acc, bf16* __restrict__ dq, int B, int T, int t_off,
+                       int rows_per_sample, int dmodel, long long ld_dq) {
+  const int groups = dmodel / 8;
+  const long long total = (long long)B * rows_per_sample * groups;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int col = (int)(idx % groups) * 8;
+    const long long row = idx / groups;
+    const long long bb = row / rows_per_sample;
+    const int tr = (int)(row % rows_per_sample);
+    const float* src = acc + ((bb * T + t_off + tr) * (long long)dmodel) + col;
+    const float4 x = *reinterpret_cast<const float4*>(src);
+    const float4 y = *reinterpret_cast<const float4*>(src + 4);
+    float v[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
+    store8(dq + row * ld_dq + col, v);
+  }
+}
+
+}  // namespace mmdit
+
+using namespace mmdit;
+
+extern "C" int mmdit_attn_bwd(const mmdit_attn_args* a, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  MMDIT_REQUIRE(a, MMDIT_ERR_ARG, "attn_bwd: null args");
+  MMDIT_REQUIRE(a->head_dim == 64, MMDIT_ERR_UNSUPPORTED, "attn_bwd: head_dim must be 64");
+  MMDIT_REQUIRE(a->B > 0 && a->H > 0 && a->N > 0 && a->M >= 0, MMDIT_ERR_ARG, "attn_bwd: bad shape");
+  MMDIT_REQUIRE(a->lse && a->delta && a->dq_acc, MMDIT_ERR_ARG,
+                "attn_bwd: lse / delta / dq_acc workspaces required");
+  AttnBwdParams p;
+  memset(&p, 0, sizeof(p));
+  const int rows[2] = {a->N, a->M};
+  const int T = a->N + a->M;
+  const int dmodel = a->H * 64;
+  cudaError_t e = cudaMemsetAsync(a->dq_acc, 0, sizeof(float) * (size_t)a->B * T * dmodel, stream);
+  if (e != cudaSuccess) {
+    set_last_error("attn_bwd: memset: %s", cudaGetErrorString(e));
+    return (int)e;
+  }
+  for (int s = 0; s < 2; ++s) {
+    if (rows[s] == 0) continue;
+    MMDIT_REQUIRE(a->q[s] && a->k[s] && a->v[s] && a->o[s] && a->d_o[s] && a->dq[s] && a->dk[s] &&
+                      a->dv[s],
+                  MMDIT_ERR_ARG, "attn_bwd: null pointer in stream %d", s);
+    MMDIT_REQUIRE(a->ld_q[s] % 8 == 0 && a->ld_k[s] % 8 == 0 && a->ld_v[s] % 8 == 0 &&
+                      a->ld_o[s] % 8 == 0 && a->ld_do[s] % 8 == 0 && a->ld_dq[s] % 8 == 0 &&
+                      a->ld_dk[s] % 8 == 0 && a->ld_dv[s] % 8 == 0,
+                  MMDIT_ERR_ALIGN, "attn_bwd: row strides must be multiples of 8 elements");
+    int rc = make_attn_tmap(&p.tmQ[s], a->q[s], a->ld_q[s], a->H, rows[s], a->B);
+    if (rc) return rc;
+    rc = make_attn_tmap(&p.tmK[s], a->k[s], a->ld_k[s], a->H, rows[s], a->B);
+    if (rc) return rc;
+    rc = make_attn_tmap(&p.tmV[s], a->v[s], a->ld_v[s], a->H, rows[s], a->B);
+    if (rc) return rc;
+    rc = make_attn_tmap(&p.tmdO[s], a->d_o[s], a->ld_do[s], a->H, rows[s], a->B);
+    if (rc) return rc;
+    p.dk[s] = static_cast<bf16*>(a->dk[s]);
+    p.dv[s] = static_cast<bf16*>(a->dv[s]);
+    p.ld_dk[s] = a->ld_dk[s];
+    p.ld_dv[s] = a->ld_dv[s];
+    // delta = rowsum(dO * O)
+    const long long nrows = (long long)a->B * rows[s];
+    const long long work = nrows * a->H * 8;
+    attn_delta_kernel<<<(unsigned)((work + 255) / 256), 256, 0, stream>>>(
+        static_cast<const bf16*>(a->o[s]), static_cast<const bf16*>(a->d_o[s]), a->delta, nrows,
+        a->H, a->ld_o[s], a->ld_do[s], rows[s], s == 0 ? 0 : a->N, T);
+  }
+  int rc = check_launch("attn_delta_kernel");
+  if (rc) return rc;
+  p.lse = a->lse; p.delta = a->delta; p.dq_acc = a->dq_acc;
+  p.B = a->B; p.H = a->H; p.N = a->N; p.M = a->M;
+  p.scale = a->scale;
+  p.scale_log2 = a->scale * 1.4426950408889634f;
+  static bool attr_set = false;
+  if (!attr_set) {
+    e = cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM);
+    if (e != cudaSuccess) {
+      set_last_error("attn_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return (int)e;
+    }
+    attr_set = true;
+  }
+  const int nt = (a->N + ATT_TILE - 1) / ATT_TILE + (a->M + ATT_TILE - 1) / ATT_TILE;
+  dim3 grid(nt, a->H, a->B);
+  attn_bwd_kernel<<<grid, BWD_THREADS, BWD_SMEM, stream>>>(p);
+  rc = check_launch("attn_bwd_kernel");
+  if (rc) return rc;
+  for (int s = 0; s < 2; ++s) {
+    if (rows[s] == 0) continue;
+    const long long work = (long long)a->B * rows[s] * (dmodel / 8);
+    long long blocks = (work + 255) / 256;
+    if (blocks > num_sms() * 16LL) blocks = num_sms() * 16LL;
+    attn_dq_convert_kernel<<<(unsigned)blocks, 256, 0, stream>>>(
+        a->dq_acc, static_cast<bf16*>(a->dq[s]), a->B, T, s == 0 ? 0 : a->N, rows[s], dmodel,
+        a->ld_dq[s]);
+  }
+  return check_launch("attn_dq_convert_kernel");
+}

@@ -1,0 +1,281 @@
+// Joint text+image softmax attention, forward, on tcgen05 tensor cores.
+// Replaces flash_attn_func (Attention.py:293) plus the concat / transpose /
+// split copies around it (Attention.py:259-263, 411-417): Q, K, V are read in
+// place from the two streams (image rows first, then text rows -- the
+// reference's concat order) through 4-D TMA descriptors, and the output is
+// written straight into the per-stream [rows, dim] buffers the out-projection
+// GEMMs consume.
+//
+// One CTA = one (sample, head, 128-query tile); two CTAs per SM so that the
+// softmax of one overlaps the MMAs of the other.  head_dim = 64.
+//   warp 0      TMA producer (Q once, then K/V tiles through a 2-deep ring)
+//   warp 1      MMA issuer: S = Q K^T (TMEM, 128 cols), O += P V (TMEM, 64 cols)
+//   warps 2..5  softmax: one thread per query row (TMEM lane), online softmax in
+//               fp32 with exp2, P written as bf16 into 128B-swizzled smem (the A
+//               operand of the second MMA), O rescaled in TMEM.
+// Tiles never straddle the image/text boundary: each stream is tiled
+// separately and partial tiles are masked, so any N, M work.
+#include "common.cuh"
+#include "mmdit_b200.h"
+
+namespace mmdit {
+
+constexpr int ATT_TILE = 128;
+constexpr int ATT_HD = 64;
+constexpr int ATT_THREADS = 192;
+constexpr int ATT_TILE_BYTES = ATT_TILE * ATT_HD * 2;  // 16 KiB
+constexpr int ATT_SMEM = 7 * ATT_TILE_BYTES + 256;     // Q, K[2], V[2], P(2 tiles) + barriers
+
+struct AttnFwdParams {
+  CUtensorMap tmQ[2], tmK[2], tmV[2];  // [0] image stream, [1] text stream
+  bf16* o[2];
+  long long ldo[2];
+  float* lse;  // [B, H, N+M]
+  int B, H, N, M;
+  float scale, scale_log2;
+};
+
+__global__ void __launch_bounds__(ATT_THREADS, 2)
+attn_fwd_kernel(const __grid_constant__ AttnFwdParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sQ = smem;
+  uint8_t* sK = smem + ATT_TILE_BYTES;
+  uint8_t* sV = smem + 3 * ATT_TILE_BYTES;
+  uint8_t* sP = smem + 5 * ATT_TILE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 7 * ATT_TILE_BYTES);
+  uint64_t* q_full = bars + 0;
+  uint64_t* kv_full = bars + 1;   // [2]
+  uint64_t* kv_empty = bars + 3;  // [2]
+  uint64_t* s_full = bars + 5;
+  uint64_t* p_full = bars + 6;
+  uint64_t* pv_done = bars + 7;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ntx = (p.N + ATT_TILE - 1) / ATT_TILE;
+  const int ntc = (p.M + ATT_TILE - 1) / ATT_TILE;
+  const int nkv = ntx + ntc;
+  const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int qs = qt < ntx ? 0 : 1;                       // stream of the query tile
+  const int q_row0 = (qs == 0 ? qt : qt - ntx) * ATT_TILE;
+  const int q_rows = qs == 0 ? p.N : p.M;
+  const int q_valid = min(ATT_TILE, q_rows - q_row0);
+
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  if (warp == 1 && lane == 0) {
+    mbar_init(q_full, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
+    mbar_init(s_full, 1);
+    mbar_init(p_full, 128);
+    mbar_init(pv_done, 1);
+    mbar_fence_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(tmem_slot, 256);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 128;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(q_full, ATT_TILE_BYTES);
+      tma_load_4d(sQ, &p.tmQ[qs], q_full, 0, h, q_row0, b);
+      for (int j = 0; j < nkv; ++j) {
+        const int st = j & 1;
+        const int ks = j < ntx ? 0 : 1;
+        const int row0 = (ks == 0 ? j : j - ntx) * ATT_TILE;
+        mbar_wait(&kv_empty[st], ((j >> 1) & 1) ^ 1);
+        mbar_expect_tx(&kv_full[st], 2 * ATT_TILE_BYTES);
+        tma_load_4d(sK + st * ATT_TILE_BYTES, &p.tmK[ks], &kv_full[st], 0, h, row0, b);
+        tma_load_4d(sV + st * ATT_TILE_BYTES, &p.tmV[ks], &kv_full[st], 0, h, row0, b);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
+      const uint32_t idesc_o = make_idesc_bf16(128, 64, 0, 1);
+      const uint32_t q_addr = smem_u32(sQ), p_addr = smem_u32(sP);
+      mbar_wait(q_full, 0);
+      for (int j = 0; j < nkv; ++j) {
+        const int st = j & 1;
+        const uint32_t k_addr = smem_u32(sK + st * ATT_TILE_BYTES);
+        const uint32_t v_addr = smem_u32(sV + st * ATT_TILE_BYTES);
+        mbar_wait(&kv_full[st], (j >> 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < ATT_HD / 16; ++k)
+          umma_bf16(tmem_S, desc_kmajor(q_addr, k), desc_kmajor(k_addr, k), idesc_s, k > 0);
+        umma_commit(s_full);
+        mbar_wait(p_full, j & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < ATT_TILE / 16; ++k)
+          umma_bf16(tmem_O, desc_kmajor(p_addr + (k >> 2) * ATT_TILE_BYTES, k & 3),
+                    desc_mnmajor(v_addr, k, ATT_TILE_BYTES), idesc_o, (j > 0 || k > 0) ? 1u : 0u);
+        umma_commit(&kv_empty[st]);
+        umma_commit(pv_done);
+      }
+    }
+  } else {
+    // ---------------------------------------------------------------- softmax
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;  // query row inside the tile == TMEM lane
+    const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
+    float m = -INFINITY, l = 0.f;
+    const float sl2 = p.scale_log2;
+    for (int j = 0; j < nkv; ++j) {
+      const int ks = j < ntx ? 0 : 1;
+      const int row0 = (ks == 0 ? j : j - ntx) * ATT_TILE;
+      const int nv = min(ATT_TILE, (ks == 0 ? p.N : p.M) - row0);  // valid keys in this tile
+      const int nchunk = (nv + 31) / 32;
+      mbar_wait(s_full, j & 1);
+      tc_fence_after();
+      float mx = -INFINITY;
+      for (int c = 0; c < nchunk; ++c) {
+        uint32_t s[32];
+        tmem_ld32(tmem_S + lane_off + c * 32, s);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (c * 32 + i < nv) mx = fmaxf(mx, __uint_as_float(s[i]));
+      }
+      const float m_new = fmaxf(m, mx);
+      const float alpha = exp2f((m - m_new) * sl2);
+      const float mb = m_new * sl2;
+      if (j > 0) {
+        mbar_wait(pv_done, (j - 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint32_t o[32];
+          tmem_ld32(tmem_O + lane_off + c * 32, o);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+          tmem_st32(tmem_O + lane_off + c * 32, o);
+        }
+        tmem_st_wait();
+      }
+      float rs = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t s[32];
+        if (c < nchunk) {
+          tmem_ld32(tmem_S + lane_off + c * 32, s);
+          tmem_ld_wait();
+        }
+        uint8_t* prow = sP + (c >> 1) * ATT_TILE_BYTES + r * 128;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          float e[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int col = c * 32 + g * 8 + i;
+            e[i] = (c < nchunk && col < nv) ? exp2f(fmaf(__uint_as_float(s[g * 8 + i]), sl2, -mb))
+                                            : 0.f;
+            rs += e[i];
+          }
+          uint4 u;
+          u.x = pack_bf16x2(e[0], e[1]); u.y = pack_bf16x2(e[2], e[3]);
+          u.z = pack_bf16x2(e[4], e[5]); u.w = pack_bf16x2(e[6], e[7]);
+          const int chunk16 = (c & 1) * 4 + g;  // 16-byte chunk inside the 128-byte row
+          *reinterpret_cast<uint4*>(prow + ((chunk16 ^ (r & 7)) << 4)) = u;
+        }
+      }
+      l = l * alpha + rs;
+      m = m_new;
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(p_full);
+    }
+    mbar_wait(pv_done, (nkv - 1) & 1);
+    tc_fence_after();
+    const float inv_l = 1.f / l;
+    const long long grow = (long long)b * q_rows + q_row0 + r;
+    bf16* orow = p.o[qs] + grow * p.ldo[qs] + h * ATT_HD;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      uint32_t o[32];
+      tmem_ld32(tmem_O + lane_off + c * 32, o);
+      tmem_ld_wait();
+      if (r < q_valid) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          float v[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(o[g * 8 + i]) * inv_l;
+          store8(orow + c * 32 + g * 8, v);
+        }
+      }
+    }
+    if (r < q_valid) {
+      const int t = (qs == 0 ? 0 : p.N) + q_row0 + r;
+      p.lse[((long long)b * p.H + h) * (p.N + p.M) + t] = m * p.scale + logf(l);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 256);
+}
+
+// 4-D view of one operand of one stream: (64 | H | rows | B), head h at column h*64.
+int make_attn_tmap(CUtensorMap* map, const void* base, long long ld, int H, int rows, int B) {
+  uint64_t dims[4] = {64, (uint64_t)H, (uint64_t)rows, (uint64_t)B};
+  uint64_t strides[3] = {64 * 2, (uint64_t)ld * 2, (uint64_t)ld * 2 * (uint64_t)rows};
+  uint32_t box[4] = {64, 1, ATT_TILE, 1};
+  return encode_tmap(map, base, 4, dims, strides, box, 2, true);
+}
+
+}  // namespace mmdit
+
+using namespace mmdit;
+
+extern "C" int mmdit_attn_fwd(const mmdit_attn_args* a, void* stream) {
+  MMDIT_REQUIRE(a, MMDIT_ERR_ARG, "attn_fwd: null args");
+  MMDIT_REQUIRE(a->head_dim == 64, MMDIT_ERR_UNSUPPORTED, "attn_fwd: head_dim must be 64, got %d",
+                a->head_dim);
+  MMDIT_REQUIRE(a->B > 0 && a->H > 0 && a->N > 0 && a->M >= 0, MMDIT_ERR_ARG, "attn_fwd: bad shape");
+  MMDIT_REQUIRE(a->q[0] && a->k[0] && a->v[0] && a->o[0] && a->lse, MMDIT_ERR_ARG,
+                "attn_fwd: null image-stream pointer");
+  MMDIT_REQUIRE(a->M == 0 || (a->q[1] && a->k[1] && a->v[1] && a->o[1]), MMDIT_ERR_ARG,
+                "attn_fwd: null text-stream pointer");
+  AttnFwdParams p;
+  memset(&p, 0, sizeof(p));
+  const int rows[2] = {a->N, a->M};
+  for (int s = 0; s < 2; ++s) {
+    if (rows[s] == 0) continue;
+    MMDIT_REQUIRE(a->ld_q[s] % 8 == 0 && a->ld_k[s] % 8 == 0 && a->ld_v[s] % 8 == 0 &&
+                      a->ld_o[s] % 8 == 0,
+                  MMDIT_ERR_ALIGN, "attn_fwd: row strides must be multiples of 8 elements");
+    int rc = make_attn_tmap(&p.tmQ[s], a->q[s], a->ld_q[s], a->H, rows[s], a->B);
+    if (rc) return rc;
+    rc = make_attn_tmap(&p.tmK[s], a->k[s], a->ld_k[s], a->H, rows[s], a->B);
+    if (rc) return rc;
+    rc = make_attn_tmap(&p.tmV[s], a->v[s], a->ld_v[s], a->H, rows[s], a->B);
+    if (rc) return rc;
+    p.o[s] = static_cast<bf16*>(a->o[s]);
+    p.ldo[s] = a->ld_o[s];
+  }
+  p.lse = a->lse;
+  p.B = a->B; p.H = a->H; p.N = a->N; p.M = a->M;
+  p.scale = a->scale;
+  p.scale_log2 = a->scale * 1.4426950408889634f;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM);
+    if (e != cudaSuccess) {
+      set_last_error("attn_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return (int)e;
+    }
+    attr_set = true;
+  }
+  const int nt = (a->N + ATT_TILE - 1) / ATT_TILE + (a->M + ATT_TILE - 1) / ATT_TILE;
+  dim3 grid(nt, a->H, a->B);
+  attn_fwd_kernel<<<grid, ATT_THREADS, ATT_SMEM, static_cast<cudaStream_t>(stream)>>>(p);
+  return check_launch("attn_fwd_kernel");
+}

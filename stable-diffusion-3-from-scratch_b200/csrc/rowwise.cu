@@ -1,0 +1,458 @@
+// Memory-bound row kernels of the MMDiT block (bf16 activations, fp32 math):
+//   adaLN LayerNorm-modulate fwd/bwd      (reference Norm.py:16-23)
+//   gate backward                          (Transformer_Block_Dual.py:64-76, autograd)
+//   text RMSNorm * scalar fwd/bwd          (diff_model.py:168-172,323-326)
+// One warp owns one row; every lane moves 128-bit vectors (8 bf16) of
+// consecutive 256-element chunks, so a warp reads/writes 512 contiguous bytes
+// per instruction.  Row statistics use warp shuffles.  Column reductions
+// (dshift/dscale/dgate, per batch element) are accumulated in registers across
+// the rows a warp owns, folded once per block in shared memory and added to
+// the fp32 output with one atomic per column per block.
+#include "common.cuh"
+#include "mmdit_b200.h"
+
+namespace mmdit {
+
+constexpr int ROW_THREADS = 256;
+constexpr int ROW_WARPS = ROW_THREADS / 32;
+
+template <int NC>
+__device__ __forceinline__ void load_row(const bf16* p, int d, int lane, float (&v)[NC][8]) {
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    const int col = c * 256 + lane * 8;
+    if (col < d) {
+      load8(p + col, v[c]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[c][j] = 0.f;
+    }
+  }
+}
+
+// ------------------------------------------------------------ LN-modulate fwd
+// y = LN(x) * bf16(1 + scale[b]) + shift[b]      (the reference adds 1 in bf16)
+template <int NC>
+__global__ void __launch_bounds__(ROW_THREADS)
+ln_mod_fwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ shift,
+                  const bf16* __restrict__ scale, bf16* __restrict__ y, float* __restrict__ mean_out,
+                  float* __restrict__ rstd_out, long long R, int d, long long rows_per_batch,
+                  long long ld_mod, float eps) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * ROW_WARPS + warp;
+  if (row >= R) return;
+  float v[NC][8];
+  load_row<NC>(x + row * d, d, lane, v);
+  float s = 0.f;
+#pragma unroll
+  for (int c = 0; c < NC; ++c)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += v[c][j];
+  const float mean = warp_sum(s) / d;
+  float q = 0.f;
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    const int col = c * 256 + lane * 8;
+    if (col < d) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float t = v[c][j] - mean;
+        q += t * t;
+      }
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(q) / d + eps);
+  if (lane == 0) {
+    if (mean_out) mean_out[row] = mean;
+    if (rstd_out) rstd_out[row] = rstd;
+  }
+  const long long b = row / rows_per_batch;
+  const bf16* sh = shift + b * ld_mod;
+  const bf16* sc = scale + b * ld_mod;
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    const int col = c * 256 + lane * 8;
+    if (col < d) {
+      float fs[8], fc[8], o[8];
+      load8(sh + col, fs);
+      load8(sc + col, fc);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float one_plus = __bfloat162float(__float2bfloat16(1.f + fc[j]));
+        o[j] = (v[c][j] - mean) * rstd * one_plus + fs[j];
+      }
+      store8(y + row * d + col, o);
+    }
+  }
+}
+
+// ------------------------------------------------------------ LN-modulate bwd
+// g = dy*(1+s); dx = rstd*(g - mean(g) - xhat*mean(g*xhat)) (+ dres)
+// dshift[b] += sum_rows dy ; dscale[b] += sum_rows dy*xhat      (fp32 atomics)
+template <int NC>
+__global__ void __launch_bounds__(ROW_THREADS)
+ln_mod_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
+                  const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
+                  const bf16* __restrict__ scale, const bf16* __restrict__ dres,
+                  bf16* __restrict__ dx, float* __restrict__ dshift, float* __restrict__ dscale,
+                  int d, long long rows_per_batch, long long ld_mod, long long ld_dmod,
+                  int rows_per_block, int blocks_per_batch) {
+  extern __shared__ float red[];  // [2][d]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long b = blockIdx.x / blocks_per_batch;
+  const int chunk = blockIdx.x % blocks_per_batch;
+  const long long r0 = b * rows_per_batch + (long long)chunk * rows_per_block;
+  long long r1 = r0 + rows_per_block;
+  if (r1 > (b + 1) * rows_per_batch) r1 = (b + 1) * rows_per_batch;
+
+  for (int i = threadIdx.x; i < 2 * d; i += ROW_THREADS) red[i] = 0.f;
+  __syncthreads();
+
+  float one_plus[NC][8];
+  {
+    const bf16* sc = scale + b * ld_mod;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      const int col = c * 256 + lane * 8;
+      if (col < d) {
+        float fc[8];
+        load8(sc + col, fc);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          one_plus[c][j] = __bfloat162float(__float2bfloat16(1.f + fc[j]));
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) one_plus[c][j] = 0.f;
+      }
+    }
+  }
+  float a_sh[NC][8], a_sc[NC][8];
+#pragma unroll
+  for (int c = 0; c < NC; ++c)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a_sh[c][j] = a_sc[c][j] = 0.f;
+
+  for (long long row = r0 + warp; row < r1; row += ROW_WARPS) {
+    float g[NC][8], xh[NC][8];
+    load_row<NC>(dy + row * d, d, lane, g);
+    load_row<NC>(x + row * d, d, lane, xh);
+    const float mean = mean_in[row], rstd = rstd_in[row];
+    float sg = 0.f, sgx = 0.f;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      const int col = c * 256 + lane * 8;
+      if (col < d) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float xhat = (xh[c][j] - mean) * rstd;
+          const float dyv = g[c][j];
+          a_sh[c][j] += dyv;
+          a_sc[c][j] += dyv * xhat;
+          const float gv = dyv * one_plus[c][j];
+          xh[c][j] = xhat;
+          g[c][j] = gv;
+          sg += gv;
+          sgx += gv * xhat;
+        }
+      }
+    }
+    const float mg = warp_sum(sg) / d, mgx = warp_sum(sgx) / d;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      const int col = c * 256 + lane * 8;
+      if (col < d) {
+        float o[8];
+        if (dres) {
+          load8(dres + row * d + col, o);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] = 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] += rstd * (g[c][j] - mg - xh[c][j] * mgx);
+        store8(dx + row * d + col, o);
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    const int col = c * 256 + lane * 8;
+    if (col < d) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        atomicAdd(&red[col + j], a_sh[c][j]);
+        atomicAdd(&red[d + col + j], a_sc[c][j]);
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < d; i += ROW_THREADS) {
+    atomicAdd(dshift + b * ld_dmod + i, red[i]);
+    atomicAdd(dscale + b * ld_dmod + i, red[d + i]);
+  }
+}
+
+// ------------------------------------------------------------------ gate bwd
+// forward was o = a*g[b] + x.  da = do*g[b]; dg[b] += sum_rows do*a;
+// dab[b] += sum_rows da (per-batch partial of the bias gradient, optional).
+template <int NC>
+__global__ void __launch_bounds__(ROW_THREADS)
+gate_bwd_kernel(const bf16* __restrict__ dout, const bf16* __restrict__ a,
+                const bf16* __restrict__ gate, bf16* __restrict__ da, float* __restrict__ dgate,
+                float* __restrict__ dab, int d, long long rows_per_batch, long long ld_gate,
+                long long ld_dgate, long long ld_dab, int rows_per_block, int blocks_per_batch) {
+  extern __shared__ float red[];  // [2][d]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long b = blockIdx.x / blocks_per_batch;
+  const int chunk = blockIdx.x % blocks_per_batch;
+  const long long r0 = b * rows_per_batch + (long long)chunk * rows_per_block;
+  long long r1 = r0 + rows_per_block;
+  if (r1 > (b + 1) * rows_per_batch) r1 = (b + 1) * rows_per_batch;
+  for (int i = threadIdx.x; i < 2 * d; i += ROW_THREADS) red[i] = 0.f;
+  __syncthreads();
+  float g[NC][8];
+  load_row<NC>(gate + b * ld_gate, d, lane, g);
+  float a_g[NC][8], a_b[NC][8];
+#pragma unroll
+  for (int c = 0; c < NC; ++c)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a_g[c][j] = a_b[c][j] = 0.f;
+  for (long long row = r0 + warp; row < r1; row += ROW_WARPS) {
+    float dv[NC][8], av[NC][8];
+    load_row<NC>(dout + row * d, d, lane, dv);
+    load_row<NC>(a + row * d, d, lane, av);
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      const int col = c * 256 + lane * 8;
+      if (col < d) {
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          a_g[c][j] += dv[c][j] * av[c][j];
+          o[j] = dv[c][j] * g[c][j];
+          a_b[c][j] += o[j];
+        }
+        store8(da + row * d + col, o);
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    const int col = c * 256 + lane * 8;
+    if (col < d) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        atomicAdd(&red[col + j], a_g[c][j]);
+        atomicAdd(&red[d + col + j], a_b[c][j]);
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < d; i += ROW_THREADS) {
+    atomicAdd(dgate + b * ld_dgate + i, red[i]);
+    if (dab) atomicAdd(dab + b * ld_dab + i, red[d + i]);
+  }
+}
+
+// ------------------------------------------------------- text RMSNorm * scalar
+// out = bf16( sigma * rmsnorm_fp32(c) * w ), first `split` tokens of every
+// sample use (w1, sigma1) and go to out1 [B*split, d]; the rest use (w2, sigma2)
+// and go to out2 [B*(M-split), d].
+template <int NC>
+__global__ void __launch_bounds__(ROW_THREADS)
+text_norm_fwd_kernel(const bf16* __restrict__ c, const float* __restrict__ w1,
+                     const float* __restrict__ w2, const float* __restrict__ sigma1,
+                     const float* __restrict__ sigma2, bf16* __restrict__ out1,
+                     bf16* __restrict__ out2, float* __restrict__ rstd_out, long long R, int d,
+                     int M, int split, float eps) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * ROW_WARPS + warp;
+  if (row >= R) return;
+  const long long b = row / M;
+  const int tok = (int)(row % M);
+  float v[NC][8];
+  load_row<NC>(c + row * d, d, lane, v);
+  float q = 0.f;
+#pragma unroll
+  for (int cc = 0; cc < NC; ++cc)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) q += v[cc][j] * v[cc][j];
+  const float rstd = rsqrtf(warp_sum(q) / d + eps);
+  if (lane == 0 && rstd_out) rstd_out[row] = rstd;
+  const bool first = tok < split;
+  const float* w = first ? w1 : w2;
+  const float sg = first ? *sigma1 : *sigma2;
+  bf16* o = first ? out1 + (b * split + tok) * (long long)d
+                  : out2 + (b * (M - split) + (tok - split)) * (long long)d;
+#pragma unroll
+  for (int cc = 0; cc < NC; ++cc) {
+    const int col = cc * 256 + lane * 8;
+    if (col < d) {
+      float r[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) r[j] = sg * (v[cc][j] * rstd * w[col + j]);
+      store8(o + col, r);
+    }
+  }
+}
+
+// backward of one half: dn = dL/d(out) [rows, d] (rows of this half, half-major),
+// dsigma += sum dn * (chat*w) ; dw[col] += sum_rows dn*chat*sigma.  No grad to c.
+template <int NC>
+__global__ void __launch_bounds__(ROW_THREADS)
+text_norm_bwd_kernel(const bf16* __restrict__ dn, const bf16* __restrict__ c,
+                     const float* __restrict__ rstd_in, const float* __restrict__ w,
+                     const float* __restrict__ sigma, float* __restrict__ dw,
+                     float* __restrict__ dsigma, long long rows, int d, int M, int tok0, int ntok,
+                     int rows_per_block) {
+  extern __shared__ float red[];  // [d]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long r0 = (long long)blockIdx.x * rows_per_block;
+  long long r1 = r0 + rows_per_block;
+  if (r1 > rows) r1 = rows;
+  for (int i = threadIdx.x; i < d; i += ROW_THREADS) red[i] = 0.f;
+  __syncthreads();
+  const float sg = *sigma;
+  float acc[NC][8];
+#pragma unroll
+  for (int cc = 0; cc < NC; ++cc)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[cc][j] = 0.f;
+  float ds = 0.f;
+  for (long long r = r0 + warp; r < r1; r += ROW_WARPS) {
+    const long long b = r / ntok;
+    const int tok = tok0 + (int)(r % ntok);
+    const long long crow = b * M + tok;
+    float g[NC][8], cv[NC][8];
+    load_row<NC>(dn + r * d, d, lane, g);
+    load_row<NC>(c + crow * d, d, lane, cv);
+    const float rstd = rstd_in[crow];
+#pragma unroll
+    for (int cc = 0; cc < NC; ++cc) {
+      const int col = cc * 256 + lane * 8;
+      if (col < d) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float chat = cv[cc][j] * rstd;
+          acc[cc][j] += g[cc][j] * chat;
+          ds += g[cc][j] * chat * w[col + j];
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int cc = 0; cc < NC; ++cc) {
+    const int col = cc * 256 + lane * 8;
+    if (col < d) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) atomicAdd(&red[col + j], acc[cc][j] * sg);
+    }
+  }
+  ds = warp_sum(ds);
+  if (lane == 0) atomicAdd(dsigma, ds);
+  __syncthreads();
+  for (int i = threadIdx.x; i < d; i += ROW_THREADS) atomicAdd(dw + i, red[i]);
+}
+
+#define DISPATCH_NC(d, CALL)                                                        \
+  do {                                                                              \
+    const int nc_ = ((d) + 255) / 256;                                              \
+    switch (nc_) {                                                                  \
+      case 1: { constexpr int NC = 1; CALL; } break;                                \
+      case 2: { constexpr int NC = 2; CALL; } break;                                \
+      case 3: { constexpr int NC = 3; CALL; } break;                                \
+      case 4: { constexpr int NC = 4; CALL; } break;                                \
+      case 5: { constexpr int NC = 5; CALL; } break;                                \
+      case 6: { constexpr int NC = 6; CALL; } break;                                \
+      case 7: { constexpr int NC = 7; CALL; } break;                                \
+      case 8: { constexpr int NC = 8; CALL; } break;                                \
+      case 9: { constexpr int NC = 9; CALL; } break;                                \
+      default:                                                                      \
+        set_last_error("row width %d unsupported (max 2304)", (int)(d));            \
+        return MMDIT_ERR_UNSUPPORTED;                                               \
+    }                                                                               \
+  } while (0)
+
+}  // namespace mmdit
+
+using namespace mmdit;
+
+extern "C" {
+
+int mmdit_ln_modulate_fwd(const void* x, const void* shift, const void* scale, void* y, float* mean,
+                          float* rstd, int64_t rows, int32_t d, int64_t rows_per_batch,
+                          int64_t ld_mod, float eps, void* stream) {
+  MMDIT_REQUIRE(x && shift && scale && y && rows > 0 && d > 0 && d % 8 == 0 && rows_per_batch > 0,
+                MMDIT_ERR_ARG, "ln_modulate_fwd: bad arguments (d must be a multiple of 8)");
+  const unsigned grid = (unsigned)((rows + ROW_WARPS - 1) / ROW_WARPS);
+  DISPATCH_NC(d, (ln_mod_fwd_kernel<NC><<<grid, ROW_THREADS, 0, (cudaStream_t)stream>>>(
+                     (const bf16*)x, (const bf16*)shift, (const bf16*)scale, (bf16*)y, mean, rstd,
+                     rows, d, rows_per_batch, ld_mod, eps)));
+  return check_launch("ln_mod_fwd_kernel");
+}
+
+int mmdit_ln_modulate_bwd(const void* dy, const void* x, const float* mean, const float* rstd,
+                          const void* scale, const void* dres, void* dx, float* dshift,
+                          float* dscale, int64_t rows, int32_t d, int64_t rows_per_batch,
+                          int64_t ld_mod, int64_t ld_dmod, void* stream) {
+  MMDIT_REQUIRE(dy && x && mean && rstd && scale && dx && dshift && dscale && rows > 0 &&
+                    d % 8 == 0 && rows_per_batch > 0 && rows % rows_per_batch == 0,
+                MMDIT_ERR_ARG, "ln_modulate_bwd: bad arguments");
+  const int rpb = 32;
+  const int bpb = (int)((rows_per_batch + rpb - 1) / rpb);
+  const unsigned grid = (unsigned)((rows / rows_per_batch) * bpb);
+  const size_t smem = 2 * (size_t)d * sizeof(float);
+  DISPATCH_NC(d, (ln_mod_bwd_kernel<NC><<<grid, ROW_THREADS, smem, (cudaStream_t)stream>>>(
+                     (const bf16*)dy, (const bf16*)x, mean, rstd, (const bf16*)scale,
+                     (const bf16*)dres, (bf16*)dx, dshift, dscale, d, rows_per_batch, ld_mod,
+                     ld_dmod, rpb, bpb)));
+  return check_launch("ln_mod_bwd_kernel");
+}
+
+int mmdit_gate_bwd(const void* dout, const void* a, const void* gate, void* da, float* dgate,
+                   float* dab, int64_t rows, int32_t d, int64_t rows_per_batch, int64_t ld_gate,
+                   int64_t ld_dgate, int64_t ld_dab, void* stream) {
+  MMDIT_REQUIRE(dout && a && gate && da && dgate && rows > 0 && d % 8 == 0 && rows_per_batch > 0 &&
+                    rows % rows_per_batch == 0,
+                MMDIT_ERR_ARG, "gate_bwd: bad arguments");
+  const int rpb = 32;
+  const int bpb = (int)((rows_per_batch + rpb - 1) / rpb);
+  const unsigned grid = (unsigned)((rows / rows_per_batch) * bpb);
+  const size_t smem = 2 * (size_t)d * sizeof(float);
+  DISPATCH_NC(d, (gate_bwd_kernel<NC><<<grid, ROW_THREADS, smem, (cudaStream_t)stream>>>(
+                     (const bf16*)dout, (const bf16*)a, (const bf16*)gate, (bf16*)da, dgate, dab, d,
+                     rows_per_batch, ld_gate, ld_dgate, ld_dab, rpb, bpb)));
+  return check_launch("gate_bwd_kernel");
+}
+
+int mmdit_text_norm_fwd(const void* c, const float* w1, const float* w2, const float* sigma1,
+                        const float* sigma2, void* out1, void* out2, float* rstd, int64_t batch,
+                        int32_t tokens, int32_t split, int32_t d, float eps, void* stream) {
+  MMDIT_REQUIRE(c && w1 && w2 && sigma1 && sigma2 && out1 && batch > 0 && tokens >= split &&
+                    split >= 0 && d % 8 == 0 && (out2 || tokens == split),
+                MMDIT_ERR_ARG, "text_norm_fwd: bad arguments");
+  const long long R = batch * (long long)tokens;
+  const unsigned grid = (unsigned)((R + ROW_WARPS - 1) / ROW_WARPS);
+  DISPATCH_NC(d, (text_norm_fwd_kernel<NC><<<grid, ROW_THREADS, 0, (cudaStream_t)stream>>>(
+                     (const bf16*)c, w1, w2, sigma1, sigma2, (bf16*)out1, (bf16*)out2, rstd, R, d,
+                     tokens, split, eps)));
+  return check_launch("text_norm_fwd_kernel");
+}
+
+int mmdit_text_norm_bwd(const void* dn, const void* c, const float* rstd, const float* w,
+                        const float* sigma, float* dw, float* dsigma, int64_t batch, int32_t tokens,
+                        int32_t tok0, int32_t ntok, int32_t d, void* stream) {
+  MMDIT_REQUIRE(dn && c && rstd && w && sigma && dw && dsigma && batch > 0 && ntok > 0 &&
+                    tok0 + ntok <= tokens && d % 8 == 0,
+                MMDIT_ERR_ARG, "text_norm_bwd: bad arguments");
+  const long long rows = batch * (long long)ntok;
+  const int rpb = 64;
+  const unsigned grid = (unsigned)((rows + rpb - 1) / rpb);
+  const size_t smem = (size_t)d * sizeof(float);
+  DISPATCH_NC(d, (text_norm_bwd_kernel<NC><<<grid, ROW_THREADS, smem, (cudaStream_t)stream>>>(
+                     (const bf16*)dn, (const bf16*)c, rstd, w, sigma, dw, dsigma, rows, d, tokens,
+                     tok0, ntok, rpb)));
+  return check_launch("text_norm_bwd_kernel");
+}
+
+}  // extern "C"

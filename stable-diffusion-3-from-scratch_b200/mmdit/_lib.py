@@ -34,6 +34,23 @@ class GemmArgs(C.Structure):
     ]
 
 
+class AttnArgs(C.Structure):
+    """Mirror of `mmdit_attn_args` (include/mmdit_b200.h)."""
+
+    _fields_ = [
+        ("q", c_vp * 2), ("k", c_vp * 2), ("v", c_vp * 2),
+        ("ld_q", c_i64 * 2), ("ld_k", c_i64 * 2), ("ld_v", c_i64 * 2),
+        ("o", c_vp * 2), ("ld_o", c_i64 * 2),
+        ("lse", c_vp),
+        ("B", c_i32), ("H", c_i32), ("N", c_i32), ("M", c_i32), ("head_dim", c_i32),
+        ("scale", c_f32),
+        ("d_o", c_vp * 2), ("ld_do", c_i64 * 2),
+        ("dq", c_vp * 2), ("dk", c_vp * 2), ("dv", c_vp * 2),
+        ("ld_dq", c_i64 * 2), ("ld_dk", c_i64 * 2), ("ld_dv", c_i64 * 2),
+        ("delta", c_vp), ("dq_acc", c_vp),
+    ]
+
+
 EPI_NONE, EPI_GATE_RESID, EPI_SILU, EPI_RESID, EPI_SWIGLU = 0, 1, 2, 3, 4
 
 _lib = None

@@ -1,0 +1,330 @@
+"""Raw (non-autograd) Python wrappers over the C-ABI kernels.
+
+Every function validates shapes/dtypes in Python (the reference's error
+convention is Python exceptions), launches on the current torch stream and
+returns torch tensors allocated by PyTorch's caching allocator.  No function
+here has a CPU or eager fallback.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import EPI_GATE_RESID, EPI_NONE, EPI_RESID, EPI_SILU  # noqa: F401
+
+BF16 = torch.bfloat16
+F32 = torch.float32
+LN_EPS = 1e-5                      # nn.LayerNorm default (Norm.py:10)
+RMS_EPS = 1.1920928955078125e-07   # nn.RMSNorm(eps=None) -> finfo(float32).eps (torch 2.11)
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("mmdit ops need CUDA tensors on a B200; there is no CPU fallback")
+
+
+def _p(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def _s():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _rowmajor2d(t, name):
+    if t.dim() != 2 or t.stride(1) != 1:
+        raise ValueError(f"{name}: expected a 2-D tensor with unit inner stride, got {tuple(t.shape)} {t.stride()}")
+
+
+# --------------------------------------------------------------------- GEMM
+def gemm(A, B, *, a_major=0, b_major=0, out=None, out_dtype=BF16, accumulate=False, split_k=0,
+         epilogue=EPI_NONE, bias=None, gate=None, rows_per_gate=0, resid=None, aux=None,
+         remap=None, out_rows=None, force_block_n=0, simt=False):
+    """D[M,N] = epilogue(A @ B^T).  A is stored [M,K] (a_major=0) or [K,M] (a_major=1);
+    B is stored [N,K] (b_major=0) or [K,N] (b_major=1)."""
+    _need_cuda(A, B)
+    _rowmajor2d(A, "A")
+    _rowmajor2d(B, "B")
+    if A.dtype != BF16 or B.dtype != BF16:
+        raise TypeError("gemm operands must be bfloat16")
+    M, K = (A.shape[1], A.shape[0]) if a_major else (A.shape[0], A.shape[1])
+    N, Kb = (B.shape[1], B.shape[0]) if b_major else (B.shape[0], B.shape[1])
+    if K != Kb:
+        raise ValueError(f"gemm: reduction dims differ ({K} vs {Kb})")
+    if out is None:
+        rows = out_rows if out_rows is not None else M
+        if remap is not None and out_rows is None:
+            raise ValueError("gemm: remap needs out_rows or out")
+        out = (torch.zeros if (accumulate or remap is not None) else torch.empty)(
+            (rows, N), device=A.device, dtype=out_dtype)
+    _rowmajor2d(out, "out")
+    a = _lib.GemmArgs()
+    a.A, a.B, a.D = A.data_ptr(), B.data_ptr(), out.data_ptr()
+    a.M, a.N, a.K = M, N, K
+    a.lda, a.ldb, a.ldd = A.stride(0), B.stride(0), out.stride(0)
+    a.a_major, a.b_major = int(a_major), int(b_major)
+    a.d_fp32 = int(out.dtype == F32)
+    a.accumulate, a.split_k, a.epilogue = int(accumulate), int(split_k), int(epilogue)
+    if bias is not None:
+        a.bias, a.bias_fp32 = bias.data_ptr(), int(bias.dtype == F32)
+    if gate is not None:
+        _rowmajor2d(gate, "gate")
+        a.gate, a.rows_per_gate, a.ld_gate = gate.data_ptr(), int(rows_per_gate), gate.stride(0)
+    if resid is not None:
+        _rowmajor2d(resid, "resid")
+        a.resid, a.ldr = resid.data_ptr(), resid.stride(0)
+    if aux is not None:
+        _rowmajor2d(aux, "aux")
+        a.aux, a.ld_aux = aux.data_ptr(), aux.stride(0)
+    if remap is not None:
+        a.remap_rows, a.remap_batch_rows, a.remap_offset = (int(x) for x in remap)
+    a.force_block_n = int(force_block_n)
+    L = _lib.lib()
+    fn = L.mmdit_gemm_bf16_simt if simt else L.mmdit_gemm_bf16
+    _lib.check(fn(C.byref(a), _s()), "mmdit_gemm_bf16")
+    return out
+
+
+# ---------------------------------------------------------------- attention
+def _fill_streams(args, name_ptr, name_ld, tensors):
+    for s, t in enumerate(tensors):
+        if t is None:
+            continue
+        _rowmajor2d(t, name_ptr)
+        getattr(args, name_ptr)[s] = t.data_ptr()
+        getattr(args, name_ld)[s] = t.stride(0)
+
+
+def attn_fwd(q, k, v, B, H, N, M, scale):
+    """q/k/v: pairs (image, text) of [B*rows, H*64] bf16 views (unit inner stride).
+    Returns (o_x [B*N,H*64], o_c [B*M,H*64] or None, lse [B,H,N+M])."""
+    _need_cuda(q[0])
+    dev, d = q[0].device, H * 64
+    o = [torch.empty((B * N, d), device=dev, dtype=BF16),
+         torch.empty((B * M, d), device=dev, dtype=BF16) if M > 0 else None]
+    lse = torch.empty((B, H, N + M), device=dev, dtype=F32)
+    a = _lib.AttnArgs()
+    _fill_streams(a, "q", "ld_q", q)
+    _fill_streams(a, "k", "ld_k", k)
+    _fill_streams(a, "v", "ld_v", v)
+    _fill_streams(a, "o", "ld_o", o)
+    a.lse = lse.data_ptr()
+    a.B, a.H, a.N, a.M, a.head_dim, a.scale = B, H, N, M, 64, float(scale)
+    _lib.check(_lib.lib().mmdit_attn_fwd(C.byref(a), _s()), "mmdit_attn_fwd")
+    return o[0], o[1], lse
+
+
+def attn_bwd(q, k, v, o, lse, d_o, dq, dk, dv, B, H, N, M, scale):
+    """Writes dq/dk/dv (pairs of [B*rows, H*64] bf16 views) for the joint attention."""
+    _need_cuda(q[0])
+    dev = q[0].device
+    T = N + M
+    delta = torch.empty((B, H, T), device=dev, dtype=F32)
+    dq_acc = torch.empty((B, T, H * 64), device=dev, dtype=F32)
+    a = _lib.AttnArgs()
+    _fill_streams(a, "q", "ld_q", q)
+    _fill_streams(a, "k", "ld_k", k)
+    _fill_streams(a, "v", "ld_v", v)
+    _fill_streams(a, "o", "ld_o", o)
+    _fill_streams(a, "d_o", "ld_do", d_o)
+    _fill_streams(a, "dq", "ld_dq", dq)
+    _fill_streams(a, "dk", "ld_dk", dk)
+    _fill_streams(a, "dv", "ld_dv", dv)
+    a.lse, a.delta, a.dq_acc = lse.data_ptr(), delta.data_ptr(), dq_acc.data_ptr()
+    a.B, a.H, a.N, a.M, a.head_dim, a.scale = B, H, N, M, 64, float(scale)
+    _lib.check(_lib.lib().mmdit_attn_bwd(C.byref(a), _s()), "mmdit_attn_bwd")
+
+
+# ------------------------------------------------------------- row kernels
+def ln_modulate_fwd(x, shift, scale, rows_per_batch, save_stats=True):
+    """x [R,d] bf16; shift/scale [B,d] bf16 views (same row stride)."""
+    _need_cuda(x)
+    R, d = x.shape
+    y = torch.empty_like(x)
+    mean = torch.empty(R, device=x.device, dtype=F32) if save_stats else None
+    rstd = torch.empty(R, device=x.device, dtype=F32) if save_stats else None
+    assert shift.stride(0) == scale.stride(0) and x.is_contiguous()
+    _lib.check(_lib.lib().mmdit_ln_modulate_fwd(
+        _p(x), _p(shift), _p(scale), _p(y), _p(mean), _p(rstd), R, d, rows_per_batch,
+        shift.stride(0), LN_EPS, _s()), "mmdit_ln_modulate_fwd")
+    return y, mean, rstd
+
+
+def ln_modulate_bwd(dy, x, mean, rstd, scale, dres, dshift, dscale, rows_per_batch):
+    """dshift/dscale: fp32 [B,d] views that are accumulated into. Returns dx bf16."""
+    R, d = x.shape
+    dx = torch.empty_like(x)
+    assert dy.is_contiguous() and x.is_contiguous() and (dres is None or dres.is_contiguous())
+    assert dshift.stride(0) == dscale.stride(0)
+    _lib.check(_lib.lib().mmdit_ln_modulate_bwd(
+        _p(dy), _p(x), _p(mean), _p(rstd), _p(scale), _p(dres), _p(dx), _p(dshift), _p(dscale),
+        R, d, rows_per_batch, scale.stride(0), dshift.stride(0), _s()), "mmdit_ln_modulate_bwd")
+    return dx
+
+
+def gate_bwd(dout, a, gate, dgate, dab, rows_per_batch):
+    R, d = dout.shape
+    da = torch.empty_like(dout)
+    assert dout.is_contiguous() and a.is_contiguous()
+    _lib.check(_lib.lib().mmdit_gate_bwd(
+        _p(dout), _p(a), _p(gate), _p(da), _p(dgate), _p(dab), R, d, rows_per_batch,
+        gate.stride(0), dgate.stride(0), 0 if dab is None else dab.stride(0), _s()),
+        "mmdit_gate_bwd")
+    return da
+
+
+def text_norm_fwd(c, w1, w2, s1, s2, split):
+    """c [B,M,dt] bf16 -> (out1 [B*split,dt], out2 [B*(M-split),dt], rstd [B*M])."""
+    _need_cuda(c)
+    Bn, M, dt = c.shape
+    assert c.is_contiguous() and c.dtype == BF16
+    out1 = torch.empty((Bn * split, dt), device=c.device, dtype=BF16)
+    out2 = torch.empty((Bn * (M - split), dt), device=c.device, dtype=BF16) if M > split else None
+    rstd = torch.empty(Bn * M, device=c.device, dtype=F32)
+    _lib.check(_lib.lib().mmdit_text_norm_fwd(
+        _p(c), _p(w1), _p(w2), _p(s1), _p(s2), _p(out1), _p(out2), _p(rstd), Bn, M, split, dt,
+        RMS_EPS, _s()), "mmdit_text_norm_fwd")
+    return out1, out2, rstd
+
+
+def text_norm_bwd(dn, c, rstd, w, sigma, dw, dsigma, tok0, ntok):
+    Bn, M, dt = c.shape
+    assert dn.is_contiguous()
+    _lib.check(_lib.lib().mmdit_text_norm_bwd(
+        _p(dn), _p(c), _p(rstd), _p(w), _p(sigma), _p(dw), _p(dsigma), Bn, M, tok0, ntok, dt,
+        _s()), "mmdit_text_norm_bwd")
+
+
+def qknorm_rope_fwd(qkv, wq, wk, rope, d, tokens_per_sample):
+    """qkv [R, >=2d] raw projections (q at col 0, k at col d). Returns [R, 2d] bf16."""
+    _need_cuda(qkv)
+    R = qkv.shape[0]
+    out = torch.empty((R, 2 * d), device=qkv.device, dtype=BF16)
+    cos, sin = rope if rope is not None else (None, None)
+    _lib.check(_lib.lib().mmdit_qknorm_rope_fwd(
+        _p(qkv), _p(wq), _p(wk), _p(cos), _p(sin), _p(out), R, d, qkv.stride(0), out.stride(0),
+        tokens_per_sample, RMS_EPS, _s()), "mmdit_qknorm_rope_fwd")
+    return out
+
+
+def qknorm_rope_bwd(dqk, qkv, wq, wk, rope, dqkv, dwq, dwk, d, tokens_per_sample):
+    R = qkv.shape[0]
+    cos, sin = rope if rope is not None else (None, None)
+    _lib.check(_lib.lib().mmdit_qknorm_rope_bwd(
+        _p(dqk), _p(qkv), _p(wq), _p(wk), _p(cos), _p(sin), _p(dqkv), _p(dwq), _p(dwk), R, d,
+        dqk.stride(0), qkv.stride(0), dqkv.stride(0), tokens_per_sample, RMS_EPS, _s()),
+        "mmdit_qknorm_rope_bwd")
+
+
+def swiglu_fwd(h12):
+    R, two_h = h12.shape
+    assert h12.is_contiguous()
+    a = torch.empty((R, two_h // 2), device=h12.device, dtype=BF16)
+    _lib.check(_lib.lib().mmdit_swiglu_fwd(_p(h12), _p(a), R, two_h // 2, _s()), "mmdit_swiglu_fwd")
+    return a
+
+
+def swiglu_bwd(da, h12, db12):
+    R, two_h = h12.shape
+    assert da.is_contiguous() and h12.is_contiguous()
+    dh12 = torch.empty_like(h12)
+    _lib.check(_lib.lib().mmdit_swiglu_bwd(_p(da), _p(h12), _p(dh12), _p(db12), R, two_h // 2, _s()),
+               "mmdit_swiglu_bwd")
+    return dh12
+
+
+def timestep_embed_fwd(t, time_scale, denom):
+    Bn, d = t.shape[0], denom.shape[0]
+    out = torch.empty((Bn, d), device=t.device, dtype=BF16)
+    _lib.check(_lib.lib().mmdit_timestep_embed_fwd(_p(t), _p(time_scale), _p(denom), _p(out), Bn, d,
+                                                   _s()), "mmdit_timestep_embed_fwd")
+    return out
+
+
+def timestep_embed_bwd(de, t, time_scale, denom, dscale):
+    Bn, d = de.shape
+    assert de.is_contiguous()
+    _lib.check(_lib.lib().mmdit_timestep_embed_bwd(_p(de), _p(t), _p(time_scale), _p(denom),
+                                                   _p(dscale), Bn, d, _s()),
+               "mmdit_timestep_embed_bwd")
+
+
+def patchify(img, p):
+    _need_cuda(img)
+    Bn, Cc, H, W = img.shape
+    assert img.is_contiguous() and img.dtype in (F32, BF16)
+    tok = torch.empty((Bn * (H // p) * (W // p), Cc * p * p), device=img.device, dtype=BF16)
+    _lib.check(_lib.lib().mmdit_patchify(_p(img), int(img.dtype == F32), _p(tok), Bn, Cc, H, W, p,
+                                         _s()), "mmdit_patchify")
+    return tok
+
+
+def unpatchify(tok, Bn, Cc, H, W, p, dtype=BF16):
+    assert tok.is_contiguous() and tok.dtype == BF16
+    img = torch.empty((Bn, Cc, H, W), device=tok.device, dtype=dtype)
+    _lib.check(_lib.lib().mmdit_unpatchify(_p(tok), _p(img), int(dtype == F32), Bn, Cc, H, W, p,
+                                           _s()), "mmdit_unpatchify")
+    return img
+
+
+def rf_noise(x0, eps, t):
+    _need_cuda(x0)
+    assert x0.dtype == eps.dtype and x0.dtype in (F32, BF16) and x0.is_contiguous()
+    xt = torch.empty(x0.shape, device=x0.device, dtype=F32)
+    _lib.check(_lib.lib().mmdit_rf_noise(_p(x0), _p(eps), int(x0.dtype == F32), _p(t), _p(xt),
+                                         x0.shape[0], x0[0].numel(), _s()), "mmdit_rf_noise")
+    return xt
+
+
+def rf_loss_fwd(v, eps, x0):
+    assert v.is_contiguous() and eps.is_contiguous() and x0.is_contiguous()
+    assert eps.dtype == x0.dtype
+    diff = torch.empty(v.shape, device=v.device, dtype=F32)
+    loss = torch.empty((), device=v.device, dtype=F32)
+    _lib.check(_lib.lib().mmdit_rf_loss_fwd(_p(v), int(v.dtype == F32), _p(eps), _p(x0),
+                                            int(x0.dtype == F32), _p(diff), _p(loss), v.numel(),
+                                            _s()), "mmdit_rf_loss_fwd")
+    return loss, diff
+
+
+def rf_loss_bwd(diff, upstream, dtype):
+    dv = torch.empty(diff.shape, device=diff.device, dtype=dtype)
+    up = upstream.to(F32).reshape(1).contiguous()
+    _lib.check(_lib.lib().mmdit_rf_loss_bwd(_p(diff), _p(up), _p(dv), int(dtype == F32),
+                                            diff.numel(), _s()), "mmdit_rf_loss_bwd")
+    return dv
+
+
+def cfg_euler_step(x, v, cfg_scale, dt):
+    """x fp32 [B,...] updated in place from v [2B,...]."""
+    assert x.dtype == F32 and x.is_contiguous() and v.is_contiguous()
+    _lib.check(_lib.lib().mmdit_cfg_euler_step(_p(x), _p(v), int(v.dtype == F32), x.numel(),
+                                               float(cfg_scale), float(dt), _s()),
+               "mmdit_cfg_euler_step")
+    return x
+
+
+def colsum(x, out=None):
+    R, n = x.shape
+    if out is None:
+        out = torch.zeros(n, device=x.device, dtype=F32)
+    _lib.check(_lib.lib().mmdit_colsum_bf16(_p(x), _p(out), R, n, x.stride(0), _s()),
+               "mmdit_colsum_bf16")
+    return out
+
+
+def fold_rows(x, out):
+    R, n = x.shape
+    _lib.check(_lib.lib().mmdit_fold_rows_f32(_p(x), _p(out), R, n, x.stride(0), _s()),
+               "mmdit_fold_rows_f32")
+    return out
+
+
+def cast_bf16(x, out=None):
+    assert x.dtype == F32 and x.is_contiguous()
+    if out is None:
+        out = torch.empty(x.shape, device=x.device, dtype=BF16)
+    _lib.check(_lib.lib().mmdit_cast_f32_bf16(_p(x), _p(out), x.numel(), _s()),
+               "mmdit_cast_f32_bf16")
+    return out

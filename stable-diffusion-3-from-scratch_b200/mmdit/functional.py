@@ -1,0 +1,316 @@
+"""torch.autograd.Function glue between the reference-shaped modules (src/) and
+the C-ABI kernels (ops.py).  Parameters stay fp32 nn.Parameters (state_dict
+contract); the kernels consume bf16 "shadow" copies that the
+modules provide, and return fp32 weight gradients through autograd, so
+torch.optim / GradScaler / clip_grad_norm_ / DDP keep working unchanged.
+
+Backward math follows SURVEY App. E (restated from the reference forward; the
+reference itself relies on autograd).
+"""
+import torch
+from torch.autograd import Function
+
+from . import ops
+from .ops import BF16, F32
+
+
+def _split_rows(t, sizes):
+    """Row slices of a packed [sum(sizes), K] tensor (views, no copies)."""
+    out, r = [], 0
+    for n in sizes:
+        out.append(t[r:r + n])
+        r += n
+    return out
+
+
+class LinearFn(Function):
+    """y = act(x @ W^T + b); W is the row-concatenation of `nw` fp32 parameters
+    (e.g. query/key/value projections, Attention.py:130-135), `wb`/`bb` are the
+    bf16 weight / fp32 bias shadows.  act: 0 none, 2 SiLU (Transformer_Block_Dual.py:25-28)."""
+
+    @staticmethod
+    def forward(ctx, x, wb, bb, act, nw, *params):
+        x2 = x.reshape(-1, x.shape[-1])
+        aux = None
+        if act == ops.EPI_SILU:  # pre-activation, needed by backward
+            aux = torch.empty((x2.shape[0], wb.shape[0]), device=x.device, dtype=BF16)
+        y = ops.gemm(x2, wb, bias=bb, epilogue=act, aux=aux)
+        ctx.save_for_backward(x2, wb, aux)
+        ctx.meta = (x.shape, act, nw, [p.shape[0] for p in params[:nw]], len(params) > nw)
+        ctx.wshapes = [p.shape for p in params[:nw]]
+        return y.reshape(*x.shape[:-1], wb.shape[0])
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, wb, aux = ctx.saved_tensors
+        xshape, act, nw, sizes, has_bias = ctx.meta
+        dy2 = dy.reshape(-1, dy.shape[-1])
+        if act == ops.EPI_SILU:
+            z = aux.float()
+            s = torch.sigmoid(z)
+            dy2 = (dy2.float() * s * (1 + z * (1 - s))).to(BF16)
+        elif not dy2.is_contiguous():
+            dy2 = dy2.contiguous()
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = ops.gemm(dy2, wb, b_major=1).reshape(xshape)
+        dw = ops.gemm(dy2, x2, a_major=1, b_major=1, out_dtype=F32)
+        grads = [g.view(shp) for g, shp in zip(_split_rows(dw, sizes), ctx.wshapes)]
+        if has_bias:
+            grads += list(_split_rows(ops.colsum(dy2), sizes))
+        return (dx, None, None, None, None, *grads)
+
+
+class GatedLinearFn(Function):
+    """o = (a @ W^T + b) * gate[sample] + resid, one GEMM with a fused epilogue
+    (out-projection / SwiGLU w3 followed by the adaLN-Zero gate and the residual,
+    Transformer_Block_Dual.py:64-76).  a: [R,K] bf16, gate: [B,N] bf16 view,
+    resid: [R,N] bf16.  The pre-gate value is kept (bf16) for dgate."""
+
+    @staticmethod
+    def forward(ctx, a, wb, bb, gate, resid, rows_per_batch, w, b):
+        R = a.shape[0]
+        aux = torch.empty((R, wb.shape[0]), device=a.device, dtype=BF16)
+        o = ops.gemm(a, wb, bias=bb, epilogue=ops.EPI_GATE_RESID, gate=gate,
+                     rows_per_gate=rows_per_batch, resid=resid, aux=aux)
+        ctx.save_for_backward(a, wb, aux, gate)
+        ctx.rpb = rows_per_batch
+        ctx.has_bias = b is not None
+        return o
+
+    @staticmethod
+    def backward(ctx, do):
+        a, wb, aux, gate = ctx.saved_tensors
+        rpb = ctx.rpb
+        do = do.contiguous()
+        Bn, n = gate.shape
+        part = torch.zeros((2, Bn, n), device=do.device, dtype=F32)
+        da = ops.gate_bwd(do, aux, gate, part[0], part[1] if ctx.has_bias else None, rpb)
+        dx = ops.gemm(da, wb, b_major=1)
+        dw = ops.gemm(da, a, a_major=1, b_major=1, out_dtype=F32)
+        db = part[1].sum(0) if ctx.has_bias else None
+        return dx, None, None, part[0].to(BF16), do, None, dw, db
+
+
+class LNModulateFn(Function):
+    """adaLN: LN(x) * (1 + scale) + shift (Norm.py:16-23). x [B,T,d] bf16; shift/scale [B,d] bf16."""
+
+    @staticmethod
+    def forward(ctx, x, shift, scale):
+        Bn, T, d = x.shape
+        x2 = x.reshape(Bn * T, d)
+        y, mean, rstd = ops.ln_modulate_fwd(x2, shift, scale, T)
+        ctx.save_for_backward(x2, mean, rstd, scale)
+        ctx.shape = (Bn, T, d)
+        return y.view(Bn, T, d)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, mean, rstd, scale = ctx.saved_tensors
+        Bn, T, d = ctx.shape
+        dmod = torch.zeros((2, Bn, d), device=dy.device, dtype=F32)
+        dx = ops.ln_modulate_bwd(dy.reshape(Bn * T, d).contiguous(), x2, mean, rstd, scale, None,
+                                 dmod[0], dmod[1], T)
+        dmod = dmod.to(BF16)
+        return dx.view(Bn, T, d), dmod[0], dmod[1]
+
+
+class JointAttentionFn(Function):
+    """QK-RMSNorm + 2-D RoPE (image tokens) + joint softmax attention over
+    [image; text] (Attention.py:130-135,174-194,259-263,293,411-417).
+    qkv_x [B*N,3d], qkv_c [B*M,3d]: packed raw projections (q | k | v)."""
+
+    @staticmethod
+    def forward(ctx, qkv_x, qkv_c, wq_x, wk_x, wq_c, wk_c, rope_cos, rope_sin, Bn, H, N, M):
+        d = H * 64
+        rope = (rope_cos, rope_sin) if rope_cos is not None else None
+        qk_x = ops.qknorm_rope_fwd(qkv_x, wq_x, wk_x, rope, d, N)
+        qk_c = ops.qknorm_rope_fwd(qkv_c, wq_c, wk_c, None, d, M)
+        q = (qk_x[:, :d], qk_c[:, :d])
+        k = (qk_x[:, d:], qk_c[:, d:])
+        v = (qkv_x[:, 2 * d:], qkv_c[:, 2 * d:])
+        o_x, o_c, lse = ops.attn_fwd(q, k, v, Bn, H, N, M, 0.125)
+        ctx.save_for_backward(qkv_x, qkv_c, qk_x, qk_c, o_x, o_c, lse, wq_x, wk_x, wq_c, wk_c,
+                              rope_cos, rope_sin)
+        ctx.dims = (Bn, H, N, M)
+        ctx.set_materialize_grads(False)
+        return o_x, o_c
+
+    @staticmethod
+    def backward(ctx, do_x, do_c):
+        (qkv_x, qkv_c, qk_x, qk_c, o_x, o_c, lse, wq_x, wk_x, wq_c, wk_c, rope_cos,
+         rope_sin) = ctx.saved_tensors
+        Bn, H, N, M = ctx.dims
+        d = H * 64
+        do_x = torch.zeros_like(o_x) if do_x is None else do_x.contiguous()
+        do_c = torch.zeros_like(o_c) if do_c is None else do_c.contiguous()
+        dqkv_x, dqkv_c = torch.empty_like(qkv_x), torch.empty_like(qkv_c)
+        dqk_x, dqk_c = torch.empty_like(qk_x), torch.empty_like(qk_c)
+        ops.attn_bwd((qk_x[:, :d], qk_c[:, :d]), (qk_x[:, d:], qk_c[:, d:]),
+                     (qkv_x[:, 2 * d:], qkv_c[:, 2 * d:]), (o_x, o_c), lse, (do_x, do_c),
+                     (dqk_x[:, :d], dqk_c[:, :d]), (dqk_x[:, d:], dqk_c[:, d:]),
+                     (dqkv_x[:, 2 * d:], dqkv_c[:, 2 * d:]), Bn, H, N, M, 0.125)
+        dw = torch.zeros((4, 64), device=qkv_x.device, dtype=F32)
+        rope = (rope_cos, rope_sin) if rope_cos is not None else None
+        ops.qknorm_rope_bwd(dqk_x, qkv_x, wq_x, wk_x, rope, dqkv_x, dw[0], dw[1], d, N)
+        ops.qknorm_rope_bwd(dqk_c, qkv_c, wq_c, wk_c, None, dqkv_c, dw[2], dw[3], d, M)
+        return dqkv_x, dqkv_c, dw[0], dw[1], dw[2], dw[3], None, None, None, None, None, None
+
+
+class SwiGLUFn(Function):
+    """a = silu(x1) * x2 with h12 = [x1 | x2] (xformers SwiGLU, MLP.py:19,32).  Also returns
+    nothing else: the bias gradient of w12 is produced by LinearFn from dh12."""
+
+    @staticmethod
+    def forward(ctx, h12):
+        shape = h12.shape
+        h2 = h12.reshape(-1, shape[-1])
+        a = ops.swiglu_fwd(h2)
+        ctx.save_for_backward(h2)
+        ctx.shape = shape
+        return a.reshape(*shape[:-1], shape[-1] // 2)
+
+    @staticmethod
+    def backward(ctx, da):
+        (h2,) = ctx.saved_tensors
+        dh = ops.swiglu_bwd(da.reshape(-1, da.shape[-1]).contiguous(), h2, None)
+        return dh.reshape(ctx.shape)
+
+
+class TimestepEmbedFn(Function):
+    """PositionalEncoding(t * time_scale) (PositionalEncoding.py:23-30, diff_model.py:306) -> bf16."""
+
+    @staticmethod
+    def forward(ctx, t, time_scale, denom):
+        t = t.to(F32).contiguous()
+        ctx.save_for_backward(t, time_scale, denom)
+        return ops.timestep_embed_fwd(t, time_scale, denom)
+
+    @staticmethod
+    def backward(ctx, de):
+        t, time_scale, denom = ctx.saved_tensors
+        ds = torch.zeros(1, device=de.device, dtype=F32)
+        ops.timestep_embed_bwd(de.contiguous(), t, time_scale, denom, ds)
+        return None, ds, None
+
+
+class TextNormFn(Function):
+    """sigma * RMSNorm(c) per encoder half (diff_model.py:323-326) -> two bf16 row blocks."""
+
+    @staticmethod
+    def forward(ctx, c, w1, w2, s1, s2, split):
+        c = c.contiguous()
+        o1, o2, rstd = ops.text_norm_fwd(c, w1, w2, s1, s2, split)
+        ctx.save_for_backward(c, rstd, w1, w2, s1, s2)
+        ctx.split = split
+        ctx.set_materialize_grads(False)
+        return o1, o2
+
+    @staticmethod
+    def backward(ctx, d1, d2):
+        c, rstd, w1, w2, s1, s2 = ctx.saved_tensors
+        split, M = ctx.split, c.shape[1]
+        dw1, dw2 = torch.zeros_like(w1), torch.zeros_like(w2)
+        ds1, ds2 = torch.zeros_like(s1), torch.zeros_like(s2)
+        if d1 is not None:
+            ops.text_norm_bwd(d1.contiguous(), c, rstd, w1, s1, dw1, ds1, 0, split)
+        if d2 is not None and M > split:
+            ops.text_norm_bwd(d2.contiguous(), c, rstd, w2, s2, dw2, ds2, split, M - split)
+        return None, dw1, dw2, ds1, ds2, None
+
+
+class ScatterRowsFn(Function):
+    """Places two row blocks ([B*n1, d], [B*n2, d]) into one [B, n1+n2, d] sequence
+    (the torch.cat at diff_model.py:323-326) -- done by the GEMM epilogue's row remap in
+    forward (see TextProjFn); this Function only exists for the standalone concat case."""
+
+    @staticmethod
+    def forward(ctx, a, b, Bn):
+        n1, n2, d = a.shape[0] // Bn, b.shape[0] // Bn, a.shape[1]
+        ctx.dims = (Bn, n1, n2, d)
+        return torch.cat([a.view(Bn, n1, d), b.view(Bn, n2, d)], 1)
+
+    @staticmethod
+    def backward(ctx, g):
+        Bn, n1, n2, d = ctx.dims
+        return (g[:, :n1].reshape(Bn * n1, d), g[:, n1:].reshape(Bn * n2, d), None)
+
+
+class TextProjFn(Function):
+    """c' = cat[c_proj(n1), c_proj2(n2)] along tokens (diff_model.py:323-326): two GEMMs whose
+    epilogues scatter rows straight into the [B, M, d] sequence."""
+
+    @staticmethod
+    def forward(ctx, n1, n2, wb1, wb2, Bn, w1, w2):
+        t1 = n1.shape[0] // Bn
+        t2 = n2.shape[0] // Bn if n2 is not None else 0
+        M, d = t1 + t2, wb1.shape[0]
+        out = torch.empty((Bn * M, d), device=n1.device, dtype=BF16)
+        ops.gemm(n1, wb1, out=out, remap=(t1, M, 0))
+        if t2:
+            ops.gemm(n2, wb2, out=out, remap=(t2, M, t1))
+        ctx.save_for_backward(n1, n2, wb1, wb2)
+        ctx.dims = (Bn, t1, t2, d)
+        return out.view(Bn, M, d)
+
+    @staticmethod
+    def backward(ctx, g):
+        n1, n2, wb1, wb2 = ctx.saved_tensors
+        Bn, t1, t2, d = ctx.dims
+        g1 = g[:, :t1].reshape(Bn * t1, d)
+        dn1 = ops.gemm(g1, wb1, b_major=1)
+        dw1 = ops.gemm(g1, n1, a_major=1, b_major=1, out_dtype=F32)
+        dn2 = dw2 = None
+        if t2:
+            g2 = g[:, t1:].reshape(Bn * t2, d)
+            dn2 = ops.gemm(g2, wb2, b_major=1)
+            dw2 = ops.gemm(g2, n2, a_major=1, b_major=1, out_dtype=F32)
+        return dn1, dn2, None, None, None, dw1, dw2
+
+
+class PatchifyFn(Function):
+    """[B,C,H,W] -> bf16 tokens [B*N, C*p*p] (the im2col of the k=s=p conv,
+    ImagePositionalEncoding.py:114-116,181-183)."""
+
+    @staticmethod
+    def forward(ctx, img, p):
+        ctx.meta = (img.shape, img.dtype, p)
+        return ops.patchify(img.contiguous(), p)
+
+    @staticmethod
+    def backward(ctx, g):
+        (Bn, Cc, H, W), dtype, p = ctx.meta
+        return ops.unpatchify(g.contiguous(), Bn, Cc, H, W, p, dtype), None
+
+
+class UnpatchifyFn(Function):
+    """tokens [B*N, C*p*p] bf16 -> [B,C,H,W] bf16 (patchify.py:41-72)."""
+
+    @staticmethod
+    def forward(ctx, tok, Bn, Cc, H, W, p):
+        ctx.p = p
+        return ops.unpatchify(tok.contiguous(), Bn, Cc, H, W, p, BF16)
+
+    @staticmethod
+    def backward(ctx, g):
+        return ops.patchify(g.contiguous(), ctx.p), None, None, None, None, None
+
+
+class RFLossFn(Function):
+    """mean((v - (eps - x0))^2) in fp32 (model_trainer.py:429-446)."""
+
+    @staticmethod
+    def forward(ctx, v, eps, x0):
+        loss, diff = ops.rf_loss_fwd(v.contiguous(), eps.contiguous(), x0.contiguous())
+        ctx.save_for_backward(diff)
+        ctx.dtype = v.dtype
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        (diff,) = ctx.saved_tensors
+        return ops.rf_loss_bwd(diff, g, ctx.dtype), None, None
+
+
+def rf_loss(v, eps, x0):
+    return RFLossFn.apply(v, eps, x0)

@@ -1,0 +1,108 @@
+"""One MMDiT dual-stream block with the reference's module API (reference:
+src/blocks/Transformer_Block_Dual.py:15-53 ctor, :56-78 forward).
+
+Same parameters and math as the reference block; the schedule is different:
+  * the 13 adaLN projections of y' (8 shift/scale, 4 gates; 9 in the last block) run as
+    ONE GEMM against a packed [13d, d] shadow weight,
+  * LN + modulate is one kernel per use,
+  * each out-projection / SwiGLU-w3 GEMM applies `* gate + residual` in its epilogue.
+checkpoint_MLP / checkpoint_attn are accepted for API compatibility; activations are kept
+instead of recomputed (180 GB of HBM3e makes recompute a pure loss at these sizes).
+"""
+import torch
+from torch import nn
+
+from mmdit import ops
+from mmdit.functional import GatedLinearFn, LinearFn
+from mmdit.shadow import packed_weight
+from src.blocks.Attention import Attention
+from src.blocks.MLP import MLP, SwiGLU
+from src.blocks.Norm import Norm, modulate
+
+BF16 = torch.bfloat16
+
+
+class Transformer_Block_Dual(nn.Module):
+    def __init__(self, dim, c_dim, hidden_scale=4.0, num_heads=8, attn_type="softmax", MLP_type="gelu",
+                 causal=False, positional_encoding="absolute", RoPE_Scale=1, kv_merge_attn=False,
+                 qk_half_dim=False, checkpoint_MLP=True, checkpoint_attn=True, layer_idx=None, last=False):
+        super().__init__()
+        if c_dim != dim:
+            raise NotImplementedError("Transformer_Block_Dual: c_dim == dim (as diff_model builds it)")
+        self.checkpoint_MLP = checkpoint_MLP
+        self.checkpoint_attn = checkpoint_attn
+        self.last = last
+        self.dim = dim
+        self.y_proj = nn.Sequential(nn.Linear(c_dim, c_dim), nn.SiLU())
+        if MLP_type == "swiglu_old":
+            self.MLP_x = SwiGLU(dim, int(dim * hidden_scale), dim)
+            if not self.last:
+                self.MLP_c = SwiGLU(dim, int(dim * hidden_scale), dim)
+        else:
+            self.MLP_x = MLP(dim, hidden_scale, act=MLP_type)
+            if not self.last:
+                self.MLP_c = MLP(dim, hidden_scale, act=MLP_type)
+        self.attn = Attention(dim, num_heads=num_heads, attn_type=attn_type, causal=causal,
+                              positional_encoding=positional_encoding, RoPE_Scale=RoPE_Scale,
+                              kv_merge_attn=kv_merge_attn, qk_half_dim=qk_half_dim, layer_idx=layer_idx,
+                              dual=True, last=last)
+        self.norm1_x = Norm(dim, c_dim)
+        self.norm2_x = Norm(dim, c_dim)
+        self.norm1_c = Norm(dim, c_dim)
+        if not self.last:
+            self.norm2_c = Norm(dim, c_dim)
+        self.scale1_x = nn.Linear(c_dim, dim, bias=False)
+        self.scale2_x = nn.Linear(c_dim, dim, bias=False)
+        if not self.last:
+            self.scale1_c = nn.Linear(c_dim, dim, bias=False)
+            self.scale2_c = nn.Linear(c_dim, dim, bias=False)
+
+    # order of the packed modulation GEMM's output slots
+    def _mod_weights(self):
+        ws = [self.norm1_x.c_shift.weight, self.norm1_x.c_scale.weight,      # 0 1
+              self.norm1_c.c_shift.weight, self.norm1_c.c_scale.weight,      # 2 3
+              self.scale1_x.weight,                                          # 4
+              self.norm2_x.c_shift.weight, self.norm2_x.c_scale.weight,      # 5 6
+              self.scale2_x.weight]                                          # 7
+        if not self.last:
+            ws += [self.scale1_c.weight,                                     # 8
+                   self.norm2_c.c_shift.weight, self.norm2_c.c_scale.weight, # 9 10
+                   self.scale2_c.weight]                                     # 11
+        return ws
+
+    @staticmethod
+    def _swiglu(mlp):
+        return mlp.MLP if isinstance(mlp, MLP) else mlp
+
+    def _gated(self, a, lin, gate, resid, rows_per_batch):
+        """resid + gate * lin(a) in one GEMM."""
+        wb = packed_weight(lin, "w", [lin.weight])
+        bb = None if lin.bias is None else lin.bias.detach()
+        B, T, d = resid.shape
+        o = GatedLinearFn.apply(a, wb, bb, gate, resid.reshape(B * T, d), rows_per_batch,
+                                lin.weight, lin.bias)
+        return o.view(B, T, d)
+
+    def forward(self, X, c, y, orig_shape):
+        B, N, d = X.shape
+        M = c.shape[1]
+        X = X if X.dtype == BF16 else X.to(BF16)
+        c = c if c.dtype == BF16 else c.to(BF16)
+        lin = self.y_proj[0]
+        yp = LinearFn.apply(y if y.dtype == BF16 else y.to(BF16), packed_weight(lin, "w", [lin.weight]),
+                            lin.bias.detach(), ops.EPI_SILU, 1, lin.weight, lin.bias)
+        ws = self._mod_weights()
+        mod = LinearFn.apply(yp, packed_weight(self, "mod", ws), None, 0, len(ws), *ws)
+        m = mod.unflatten(1, (len(ws), d)).unbind(1)
+
+        a_x, a_c = self.attn.attend(modulate(X, m[0], m[1]), modulate(c, m[2], m[3]), orig_shape)
+        X = self._gated(a_x, self.attn.out_proj_x, m[4], X, N)
+        if not self.last:
+            c = self._gated(a_c, self.attn.out_proj_c, m[8], c, M)
+
+        mx = self._swiglu(self.MLP_x)
+        X = self._gated(mx.hidden(modulate(X, m[5], m[6])).reshape(B * N, -1), mx.w3, m[7], X, N)
+        if not self.last:
+            mc = self._swiglu(self.MLP_c)
+            c = self._gated(mc.hidden(modulate(c, m[9], m[10])).reshape(B * M, -1), mc.w3, m[11], c, M)
+        return X, c

@@ -30,6 +30,8 @@ const char* mmdit_last_error(void);
 int mmdit_abi_version(void);
 /* 0 when the current CUDA device is sm_100 (B200); error otherwise. */
 int mmdit_device_check(void);
+/* Number of CUDA kernels this library has launched in this process (bench.py's gpu_launches). */
+unsigned long long mmdit_launch_count(void);
 
 /* ------------------------------------------------------------------ GEMM --
  * D[M,N] = epilogue( A[M,K] * B[N,K]^T )  on tcgen05 tensor cores, fp32

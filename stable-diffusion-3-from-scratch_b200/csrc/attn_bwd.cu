@@ -358,7 +358,7 @@ extern "C" int mmdit_attn_bwd(const mmdit_attn_args* a, void* stream_) {
         static_cast<const bf16*>(a->o[s]), static_cast<const bf16*>(a->d_o[s]), a->delta, nrows,
         a->H, a->ld_o[s], a->ld_do[s], rows[s], s == 0 ? 0 : a->N, T);
   }
-  int rc = check_launch("attn_delta_kernel");
+  int rc = check_launch("attn_delta_kernel", a->M > 0 ? 2 : 1);
   if (rc) return rc;
   p.lse = a->lse; p.delta = a->delta; p.dq_acc = a->dq_acc;
   p.B = a->B; p.H = a->H; p.N = a->N; p.M = a->M;
@@ -387,5 +387,5 @@ extern "C" int mmdit_attn_bwd(const mmdit_attn_args* a, void* stream_) {
         a->dq_acc, static_cast<bf16*>(a->dq[s]), a->B, T, s == 0 ? 0 : a->N, rows[s], dmodel,
         a->ld_dq[s]);
   }
-  return check_launch("attn_dq_convert_kernel");
+  return check_launch("attn_dq_convert_kernel", a->M > 0 ? 2 : 1);
 }

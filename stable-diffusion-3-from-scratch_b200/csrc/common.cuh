@@ -21,7 +21,7 @@ enum {
   MMDIT_ERR_DRIVER = -4,
 };
 void set_last_error(const char* fmt, ...);
-int check_launch(const char* what);  // cudaGetLastError -> code + message
+int check_launch(const char* what, int kernels = 1);  // cudaGetLastError -> code + message; counts launches
 
 #define MMDIT_REQUIRE(cond, code, ...)  \
   do {                                  \

@@ -19,7 +19,10 @@ void set_last_error(const char* fmt, ...) {
   va_end(ap);
 }
 
-int check_launch(const char* what) {
+static unsigned long long g_launches = 0;
+
+int check_launch(const char* what, int kernels) {
+  __atomic_fetch_add(&g_launches, (unsigned long long)kernels, __ATOMIC_RELAXED);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     set_last_error("%s: %s", what, cudaGetErrorString(e));
@@ -95,6 +98,10 @@ extern "C" {
 const char* mmdit_last_error(void) { return mmdit::g_err; }
 
 int mmdit_abi_version(void) { return MMDIT_ABI_VERSION; }
+
+unsigned long long mmdit_launch_count(void) {
+  return __atomic_load_n(&mmdit::g_launches, __ATOMIC_RELAXED);
+}
 
 int mmdit_device_check(void) {
   int dev = 0;

@@ -70,6 +70,7 @@ def lib():
     L.mmdit_last_error.argtypes = []
     L.mmdit_abi_version.restype = c_i32
     L.mmdit_device_check.restype = c_i32
+    L.mmdit_launch_count.restype = C.c_ulonglong
     _declare(L)
     _lib = L
     return L
@@ -95,3 +96,8 @@ def stream_ptr():
 
 def ptr(t):
     return 0 if t is None else t.data_ptr()
+
+
+def launch_count():
+    """CUDA kernels launched by the library so far in this process."""
+    return int(lib().mmdit_launch_count())

@@ -29,6 +29,8 @@ def _p(t):
 
 
 def _s():
+    if not torch.cuda.is_available():
+        raise RuntimeError("mmdit ops need CUDA tensors on a B200; there is no CPU fallback")
     return torch.cuda.current_stream().cuda_stream
 
 

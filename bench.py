@@ -163,6 +163,7 @@ def instrument_kernels(trainer, batch):
     import mmdit.functional as Fn
     try:
         trainer._zero()
+        torch.cuda._sleep(int(4e8))   # keep the GPU busy while the host enqueues: events then time kernels, not launch gaps
         trainer._fwd_bwd(batch)
         torch.cuda.synchronize()
     finally:

@@ -26,6 +26,7 @@ constexpr int MAX_STAGES = 8;
 constexpr int GEMM_THREADS = 256;
 constexpr int SMEM_BUDGET = 227 * 1024;
 constexpr int BAR_BYTES = 256;
+constexpr int EPI_STAGE_BYTES = 4 * 32 * 64 * 4;  // 4 warps x (32 rows x 64 fp32)
 
 struct GemmParams {
   CUtensorMap tmA, tmB;
@@ -46,6 +47,7 @@ struct GemmParams {
   bf16* aux;
   long long ld_aux;
   long long remap_rows, remap_batch_rows, remap_offset;
+  int debug;  // bit0: skip global stores, bit1: skip TMEM loads (perf experiments only)
 };
 
 __device__ __forceinline__ float bias_at(const GemmParams& p, int n) {
@@ -74,7 +76,8 @@ __device__ __forceinline__ void epilogue8(const GemmParams& p, long long m, long
   if (p.epi == MMDIT_EPI_GATE_RESID || p.epi == MMDIT_EPI_RESID) {
     float g[8], r[8];
     if (p.epi == MMDIT_EPI_GATE_RESID) {
-      const bf16* gp = p.gate + (m / p.rows_per_gate) * p.ld_gate + n;
+      const bf16* gp = p.gate +
+          static_cast<long long>(static_cast<unsigned>(m) / static_cast<unsigned>(p.rows_per_gate)) * p.ld_gate + n;
       if (full && ((reinterpret_cast<uintptr_t>(gp) & 15) == 0)) {
         load8(gp, g);
       } else {
@@ -126,6 +129,66 @@ __device__ __forceinline__ void epilogue8(const GemmParams& p, long long m, long
   }
 }
 
+// Epilogue variants.  The fast ones are straight-line code for the hot GEMMs of the block
+// (all run-time flags resolved at compile time, full 8-column vectors, 16-byte aligned rows);
+// EV_GENERIC keeps every option behind run-time flags (tails, remap, SiLU, odd alignments).
+enum { EV_GENERIC = 0, EV_BF16 = 1, EV_BF16_BIAS = 2, EV_GATE = 3, EV_F32 = 4, EV_F32_ATOMIC = 5 };
+
+template <int EV>
+__device__ __forceinline__ void epilogue_fast(const GemmParams& p, const float* wbuf, int lane,
+                                              long long m0, int n) {
+  const int sub_row = lane >> 3, seg = lane & 7;
+  float bias[8];
+  if constexpr (EV == EV_BF16_BIAS || EV == EV_GATE) {
+    if (p.bias) {
+      const float4 b0 = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.bias) + n);
+      const float4 b1 = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.bias) + n + 4);
+      bias[0] = b0.x; bias[1] = b0.y; bias[2] = b0.z; bias[3] = b0.w;
+      bias[4] = b1.x; bias[5] = b1.y; bias[6] = b1.z; bias[7] = b1.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) bias[j] = 0.f;
+    }
+  }
+#pragma unroll
+  for (int pass = 0; pass < 8; ++pass) {
+    const int row = pass * 4 + sub_row;
+    const long long m = m0 + row;
+    const float4* rrow = reinterpret_cast<const float4*>(wbuf + row * 64);
+    const float4 a = rrow[(2 * seg) ^ (row & 7)];
+    const float4 b = rrow[(2 * seg + 1) ^ (row & 7)];
+    if (m >= p.M) continue;
+    float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    if constexpr (EV == EV_BF16_BIAS || EV == EV_GATE) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] += bias[j];
+    }
+    if constexpr (EV == EV_GATE) {
+      store8(p.aux + m * p.ld_aux + n, v);  // pre-gate value, needed for dgate
+      float g[8], r[8];
+      const unsigned gb = static_cast<unsigned>(m) / static_cast<unsigned>(p.rows_per_gate);
+      load8(p.gate + static_cast<long long>(gb) * p.ld_gate + n, g);
+      load8(p.resid + m * p.ldr + n, r);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], g[j], r[j]);
+    }
+    if constexpr (EV == EV_BF16 || EV == EV_BF16_BIAS || EV == EV_GATE) {
+      store8(reinterpret_cast<bf16*>(p.D) + m * p.ldd + n, v);
+    } else if constexpr (EV == EV_F32) {
+      float* dp = reinterpret_cast<float*>(p.D) + m * p.ldd + n;
+      *reinterpret_cast<float4*>(dp) = make_float4(v[0], v[1], v[2], v[3]);
+      *reinterpret_cast<float4*>(dp + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    } else if constexpr (EV == EV_F32_ATOMIC) {
+      float* dp = reinterpret_cast<float*>(p.D) + m * p.ldd + n;
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dp), "f"(v[0]), "f"(v[1]),
+                   "f"(v[2]), "f"(v[3]) : "memory");
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dp + 4), "f"(v[4]), "f"(v[5]),
+                   "f"(v[6]), "f"(v[7]) : "memory");
+    }
+  }
+}
+
+template <int EV>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -140,7 +203,9 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
   const int stage_bytes = A_STAGE_BYTES + b_stage_bytes;
   const int stages = p.stages;
 
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + stages * stage_bytes);
+  // epilogue staging: per epilogue warp 32 rows x 64 fp32 (16-byte chunks XOR-swizzled by row)
+  uint8_t* stage_buf = smem + stages * stage_bytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(stage_buf + EPI_STAGE_BYTES);
   uint64_t* empty_bar = full_bar + MAX_STAGES;
   uint64_t* tmem_full = empty_bar + MAX_STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
@@ -253,33 +318,61 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
       const int m_blk = tile % p.tiles_m, n_blk = tile / p.tiles_m;
       mbar_wait(&tmem_full[as], aphase);
       tc_fence_after();
-      const long long m = static_cast<long long>(m_blk) * BLOCK_M + ew * 32 + lane;
-      long long drow = m;
-      if (p.remap_rows > 0)
-        drow = (m / p.remap_rows) * p.remap_batch_rows + (m % p.remap_rows) + p.remap_offset;
+      // Accumulator rows live one per thread (TMEM lane).  Each 64-column chunk is transposed
+      // through shared memory so that 8 lanes cover one row's 64 columns: every global load /
+      // store of the fused epilogue is then a full, coalesced 128-byte (bf16) line per row.
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + as * block_n;
-      for (int c = 0; c < block_n / 32; ++c) {
-        uint32_t r[32];
-        tmem_ld32(taddr + c * 32, r);
-        tmem_ld_wait();
-        const int n0 = n_blk * block_n + c * 32;
-        if (m < p.M && n0 < p.N) {
+      float* wbuf = reinterpret_cast<float*>(stage_buf + ew * (32 * 64 * 4));
+      const int nchunks = block_n / 64;
+      const int sub_row = lane >> 3, seg = lane & 7;
+      for (int c = 0; c < nchunks; ++c) {
+        uint32_t r0[32], r1[32];
+        if (!(p.debug & 2)) {
+          tmem_ld32(taddr + c * 64, r0);
+          tmem_ld32(taddr + c * 64 + 32, r1);
+          tmem_ld_wait();
+        }
+        if (c == nchunks - 1) {  // accumulator fully drained: hand the TMEM stage back early
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty[as]);
+        }
+        float4* wrow = reinterpret_cast<float4*>(wbuf + lane * 64);
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const int n = n0 + g * 8;
-            const int nvalid = min(8, p.N - n);
-            if (nvalid > 0) {
-              float v[8];
-#pragma unroll
-              for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g * 8 + j]);
+        for (int j = 0; j < 8; ++j) {
+          wrow[j ^ (lane & 7)] = make_float4(__uint_as_float(r0[4 * j]), __uint_as_float(r0[4 * j + 1]),
+                                             __uint_as_float(r0[4 * j + 2]), __uint_as_float(r0[4 * j + 3]));
+          wrow[(8 + j) ^ (lane & 7)] =
+              make_float4(__uint_as_float(r1[4 * j]), __uint_as_float(r1[4 * j + 1]),
+                          __uint_as_float(r1[4 * j + 2]), __uint_as_float(r1[4 * j + 3]));
+        }
+        __syncwarp();
+        const int n = n_blk * block_n + c * 64 + seg * 8;
+        if constexpr (EV != EV_GENERIC) {
+          if (n < p.N && !(p.debug & 1))
+            epilogue_fast<EV>(p, wbuf, lane, static_cast<long long>(m_blk) * BLOCK_M + ew * 32, n);
+        } else {
+          const int nvalid = min(8, p.N - n);
+#pragma unroll 1
+          for (int pass = 0; pass < 8; ++pass) {
+            const int row = pass * 4 + sub_row;
+            const long long m = static_cast<long long>(m_blk) * BLOCK_M + ew * 32 + row;
+            const float4* rrow = reinterpret_cast<const float4*>(wbuf + row * 64);
+            const float4 a = rrow[(2 * seg) ^ (row & 7)];
+            const float4 b = rrow[(2 * seg + 1) ^ (row & 7)];
+            if (m < p.M && nvalid > 0 && !(p.debug & 1)) {
+              long long drow = m;
+              if (p.remap_rows > 0) {
+                const unsigned mm = static_cast<unsigned>(m), rr = static_cast<unsigned>(p.remap_rows);
+                drow = static_cast<long long>(mm / rr) * p.remap_batch_rows + (mm % rr) + p.remap_offset;
+              }
+              float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
               epilogue8(p, m, drow, n, v, nvalid);
             }
           }
         }
+        __syncwarp();  // staging buffer is reused by the next chunk
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[as]);
       as ^= 1;
       if (as == 0) aphase ^= 1;
     }
@@ -339,7 +432,7 @@ extern "C" int mmdit_gemm_bf16(const mmdit_gemm_args* a, void* stream_) {
   MMDIT_REQUIRE(p.block_n == 64 || p.block_n == 128 || p.block_n == 256, MMDIT_ERR_ARG,
                 "gemm: block_n %d", p.block_n);
   const int stage_bytes = A_STAGE_BYTES + p.block_n * BLOCK_K * 2;
-  p.stages = (SMEM_BUDGET - 1024 - BAR_BYTES) / stage_bytes;
+  p.stages = (SMEM_BUDGET - 1024 - BAR_BYTES - EPI_STAGE_BYTES) / stage_bytes;
   if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
   p.tiles_m = (p.M + BLOCK_M - 1) / BLOCK_M;
   p.tiles_n = (p.N + p.block_n - 1) / p.block_n;
@@ -369,6 +462,7 @@ extern "C" int mmdit_gemm_bf16(const mmdit_gemm_args* a, void* stream_) {
   p.aux = static_cast<bf16*>(a->aux); p.ld_aux = a->ld_aux;
   p.remap_rows = a->remap_rows; p.remap_batch_rows = a->remap_batch_rows;
   p.remap_offset = a->remap_offset;
+  p.debug = a->reserved;
 
   // Tensor maps. dims are innermost-first.
   {
@@ -386,19 +480,53 @@ extern "C" int mmdit_gemm_bf16(const mmdit_gemm_args* a, void* stream_) {
     if (rc) return rc;
   }
 
-  const int smem_bytes = p.stages * stage_bytes + BAR_BYTES + 1024;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET);
-    if (e != cudaSuccess) {
-      set_last_error("gemm: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-      return (int)e;
-    }
-    attr_set = true;
-  }
+  const int smem_bytes = p.stages * stage_bytes + EPI_STAGE_BYTES + BAR_BYTES + 1024;
   const int total_work = tiles * p.split_k;
   const int grid = total_work < sms ? total_work : sms;
-  gemm_tcgen05_kernel<<<grid, GEMM_THREADS, smem_bytes, stream>>>(p);
+
+  // pick the epilogue variant: fast paths need whole 16-byte vectors everywhere
+  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  const bool vec_ok = a->N % 8 == 0 && al16(a->D) && a->remap_rows == 0 &&
+                      (a->d_fp32 ? a->ldd % 4 == 0 : a->ldd % 8 == 0);
+  const bool bias_ok = !a->bias || (a->bias_fp32 && al16(a->bias));
+  int ev = EV_GENERIC;
+  if (vec_ok && !a->reserved) {
+    if (a->d_fp32) {
+      if (a->epilogue == MMDIT_EPI_NONE && !a->bias && !a->aux) {
+        if (!a->accumulate) ev = EV_F32;
+        else if (p.split_k > 1 || a->accumulate) ev = EV_F32_ATOMIC;  // red.add is also a valid "+="
+      }
+    } else if (a->epilogue == MMDIT_EPI_NONE && !a->aux) {
+      if (!a->bias) ev = EV_BF16;
+      else if (bias_ok) ev = EV_BF16_BIAS;
+    } else if (a->epilogue == MMDIT_EPI_GATE_RESID && a->aux && bias_ok && al16(a->aux) &&
+               al16(a->gate) && al16(a->resid) && a->ld_aux % 8 == 0 && a->ld_gate % 8 == 0 &&
+               a->ldr % 8 == 0) {
+      ev = EV_GATE;
+    }
+  }
+#define LAUNCH_EV(EVV)                                                                            \
+  case EVV: {                                                                                     \
+    static bool attr_set = false;                                                                 \
+    if (!attr_set) {                                                                              \
+      cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<EVV>,                              \
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET); \
+      if (e != cudaSuccess) {                                                                     \
+        set_last_error("gemm: cudaFuncSetAttribute: %s", cudaGetErrorString(e));                  \
+        return (int)e;                                                                            \
+      }                                                                                           \
+      attr_set = true;                                                                            \
+    }                                                                                             \
+    gemm_tcgen05_kernel<EVV><<<grid, GEMM_THREADS, smem_bytes, stream>>>(p);                      \
+  } break;
+  switch (ev) {
+    LAUNCH_EV(EV_GENERIC)
+    LAUNCH_EV(EV_BF16)
+    LAUNCH_EV(EV_BF16_BIAS)
+    LAUNCH_EV(EV_GATE)
+    LAUNCH_EV(EV_F32)
+    LAUNCH_EV(EV_F32_ATOMIC)
+  }
+#undef LAUNCH_EV
   return check_launch("gemm_tcgen05_kernel");
 }

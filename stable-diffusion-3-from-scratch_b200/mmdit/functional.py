@@ -314,3 +314,28 @@ class RFLossFn(Function):
 
 def rf_loss(v, eps, x0):
     return RFLossFn.apply(v, eps, x0)
+
+
+class SwiGLUHiddenFn(Function):
+    """a = silu(x1) * x2 with [x1 | x2] = x @ W12^T + b12 (xformers SwiGLU up to w3, MLP.py:19,32).
+    One Function so that the bias gradient of w12 falls out of the activation-backward kernel
+    instead of a second pass over dh12."""
+
+    @staticmethod
+    def forward(ctx, x, wb, w12, b12):
+        x2 = x.reshape(-1, x.shape[-1])
+        h12 = ops.gemm(x2, wb, bias=None if b12 is None else b12.detach())
+        a = ops.swiglu_fwd(h12)
+        ctx.save_for_backward(x2, wb, h12)
+        ctx.meta = (x.shape, b12 is not None)
+        return a.reshape(*x.shape[:-1], a.shape[-1])
+
+    @staticmethod
+    def backward(ctx, da):
+        x2, wb, h12 = ctx.saved_tensors
+        xshape, has_bias = ctx.meta
+        db = torch.zeros(h12.shape[1], device=da.device, dtype=F32) if has_bias else None
+        dh = ops.swiglu_bwd(da.reshape(-1, da.shape[-1]).contiguous(), h12, db)
+        dx = ops.gemm(dh, wb, b_major=1).reshape(xshape)
+        dw = ops.gemm(dh, x2, a_major=1, b_major=1, out_dtype=F32)
+        return dx, None, dw, db

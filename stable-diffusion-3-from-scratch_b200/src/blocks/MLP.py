@@ -5,7 +5,7 @@ MLP.w12.{weight,bias}, MLP.w3.{weight,bias}."""
 import torch
 from torch import nn
 
-from mmdit.functional import LinearFn, SwiGLUFn
+from mmdit.functional import LinearFn, SwiGLUHiddenFn
 from mmdit.shadow import packed_weight
 
 BF16 = torch.bfloat16
@@ -22,10 +22,7 @@ class SwiGLU(nn.Module):
     def hidden(self, X):
         """silu(x1) * x2 -- everything before w3 (the block fuses w3 with gate + residual)."""
         wb = packed_weight(self, "w12", [self.w12.weight])
-        params = [self.w12.weight] + ([self.w12.bias] if self.w12.bias is not None else [])
-        h12 = LinearFn.apply(X if X.dtype == BF16 else X.to(BF16), wb,
-                             None if self.w12.bias is None else self.w12.bias.detach(), 0, 1, *params)
-        return SwiGLUFn.apply(h12)
+        return SwiGLUHiddenFn.apply(X if X.dtype == BF16 else X.to(BF16), wb, self.w12.weight, self.w12.bias)
 
     def forward(self, X):
         a = self.hidden(X)

@@ -134,6 +134,10 @@ int mmdit_ln_modulate_bwd(const void* dy, const void* x, const float* mean, cons
 /* Backward of the gated residual o = a * gate[b] + x (Transformer_Block_Dual.py:64-76):
  * da = dout * gate[b]; dgate[b] += sum_rows dout * a; dab[b] += sum_rows da (optional,
  * per-sample partial of the bias gradient of the producing linear). fp32 outputs accumulate. */
+/* Forward of the same gated residual as a standalone kernel: out = a * gate[b] + resid. */
+int mmdit_gate_residual_fwd(const void* a, const void* gate, const void* resid, void* out,
+                            int64_t rows, int32_t d, int64_t rows_per_batch, int64_t ld_gate,
+                            void* stream);
 int mmdit_gate_bwd(const void* dout, const void* a, const void* gate, void* da, float* dgate,
                    float* dab, int64_t rows, int32_t d, int64_t rows_per_batch, int64_t ld_gate,
                    int64_t ld_dgate, int64_t ld_dab, void* stream);

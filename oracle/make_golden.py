@@ -64,12 +64,18 @@ def main():
         C = cfg["model"]["inCh"]
         batch = O.synth_batch(cfg["B"], C, cfg["h"], cfg["w"], cfg["M"], seed=1000)
         out = dict(config=cfg, shapes=shapes)
+        gsave = {}
         for tag, ac in (("fp32", False), ("bf16", True)):
             v, loss, grads = ref_step(model, batch, ac)
+            gsave[tag] = grads
             out[f"v_{tag}"] = v
             out[f"loss_{tag}"] = loss
             out[f"gradnorm_{tag}"] = {k: float(g.norm()) for k, g in grads.items()}
             out[f"grads_{tag}"] = {k: grads[k] for k in FULL_GRADS if k in grads}
+        # the reference's own bf16-autocast error per parameter gradient (max-abs err / max-abs fp32)
+        out["grad_relerr_bf16"] = {
+            k: float((gsave["bf16"][k].float() - g32).abs().max() / (g32.abs().max() + 1e-30))
+            for k, g32 in gsave["fp32"].items() if k in gsave["bf16"]}
         # loss trajectory of the restated train step (fp32, AdamW 1e-4, clip 1.0), 8 steps
         opt = torch.optim.AdamW(model.parameters(), lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01)
         traj = []

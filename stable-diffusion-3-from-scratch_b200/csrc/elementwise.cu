@@ -248,6 +248,28 @@ swiglu_bwd_kernel(const bf16* __restrict__ da, const bf16* __restrict__ h12,
   }
 }
 
+// ------------------------------------------------------------ gated residual
+// out[r,:] = a[r,:] * gate[r / rows_per_batch, :] + resid[r,:]   (Transformer_Block_Dual.py:64-76)
+__global__ void __launch_bounds__(256)
+gate_residual_fwd_kernel(const bf16* __restrict__ a, const bf16* __restrict__ gate,
+                         const bf16* __restrict__ resid, bf16* __restrict__ out, long long R, int d,
+                         long long rows_per_batch, long long ld_gate) {
+  const int groups = d / 8;
+  const long long total = R * groups;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long row = idx / groups;
+    const int col = (int)(idx % groups) * 8;
+    float av[8], gv[8], rv[8], o[8];
+    load8(a + row * d + col, av);
+    load8(resid + row * d + col, rv);
+    load8(gate + (row / rows_per_batch) * ld_gate + col, gv);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = fmaf(av[j], gv[j], rv[j]);
+    store8(out + row * d + col, o);
+  }
+}
+
 // ------------------------------------------------------------ timestep embed
 // e[b, j]      = sin(t_b * s / den[2j])        j <  d/2
 // e[b, d/2+j]  = cos(t_b * s / den[2j+1])
@@ -464,6 +486,19 @@ int mmdit_qknorm_rope_bwd(const void* dqk, const void* qkv, const float* wq, con
       (const bf16*)dqk, (const bf16*)qkv, wq, wk, rope_cos, rope_sin, (bf16*)dqkv, dwq, dwk, rows,
       d, ld_g, ld_in, ld_dout, tokens_per_sample, eps);
   return check_launch("qknorm_rope_bwd_kernel");
+}
+
+int mmdit_gate_residual_fwd(const void* a, const void* gate, const void* resid, void* out,
+                            int64_t rows, int32_t d, int64_t rows_per_batch, int64_t ld_gate,
+                            void* stream) {
+  MMDIT_REQUIRE(a && gate && resid && out && rows > 0 && d > 0 && d % 8 == 0 && rows_per_batch > 0 &&
+                    ld_gate % 8 == 0,
+                MMDIT_ERR_ARG, "gate_residual_fwd: bad arguments");
+  const long long work = rows * (long long)(d / 8);
+  gate_residual_fwd_kernel<<<grid_for(work, 256), 256, 0, (cudaStream_t)stream>>>(
+      (const bf16*)a, (const bf16*)gate, (const bf16*)resid, (bf16*)out, rows, d, rows_per_batch,
+      ld_gate);
+  return check_launch("gate_residual_fwd_kernel");
 }
 
 int mmdit_swiglu_fwd(const void* h12, void* a, int64_t rows, int32_t hidden, void* stream) {

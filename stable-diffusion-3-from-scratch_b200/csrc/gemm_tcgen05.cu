@@ -14,6 +14,8 @@
 // operands may be K-major or MN-major (see mmdit_b200.h), which gives fprop,
 // dgrad and wgrad from the same kernel without transposed copies.  Split-K
 // (fp32 atomics) keeps all SMs busy on the small-output / long-reduction wgrads.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "mmdit_b200.h"
 
@@ -134,9 +136,37 @@ __device__ __forceinline__ void epilogue8(const GemmParams& p, long long m, long
 // EV_GENERIC keeps every option behind run-time flags (tails, remap, SiLU, odd alignments).
 enum { EV_GENERIC = 0, EV_BF16 = 1, EV_BF16_BIAS = 2, EV_GATE = 3, EV_F32 = 4, EV_F32_ATOMIC = 5 };
 
+// Operands of the gated-residual epilogue for one 64-column chunk: 8 passes x (gate, resid),
+// loaded as a batch (and before the accumulator is needed) so their latency is paid once.
+// 16-byte streaming load that does not allocate in L1 (which is almost entirely carved out as
+// shared memory here, so allocating loads would serialise on a few KB of cache).
+__device__ __forceinline__ uint4 ld_stream16(const void* ptr) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(ptr));
+  return r;
+}
+struct GatePrefetch {
+  uint4 g[8], r[8];
+};
+__device__ __forceinline__ void gate_prefetch(const GemmParams& p, int lane, long long m0, int n,
+                                              GatePrefetch& pf) {
+  const int sub_row = lane >> 3;
+#pragma unroll
+  for (int pass = 0; pass < 8; ++pass) {
+    const long long m = m0 + pass * 4 + sub_row;
+    if (m < p.M && n < p.N && !(p.debug & 8)) {
+      const unsigned gb = static_cast<unsigned>(m) / static_cast<unsigned>(p.rows_per_gate);
+      pf.g[pass] = __ldg(reinterpret_cast<const uint4*>(p.gate + static_cast<long long>(gb) * p.ld_gate + n));
+      pf.r[pass] = ld_stream16(p.resid + m * p.ldr + n);
+    }
+  }
+}
+
 template <int EV>
 __device__ __forceinline__ void epilogue_fast(const GemmParams& p, const float* wbuf, int lane,
-                                              long long m0, int n) {
+                                              long long m0, int n, const GatePrefetch* pf) {
   const int sub_row = lane >> 3, seg = lane & 7;
   float bias[8];
   if constexpr (EV == EV_BF16_BIAS || EV == EV_GATE) {
@@ -164,13 +194,16 @@ __device__ __forceinline__ void epilogue_fast(const GemmParams& p, const float* 
       for (int j = 0; j < 8; ++j) v[j] += bias[j];
     }
     if constexpr (EV == EV_GATE) {
-      store8(p.aux + m * p.ld_aux + n, v);  // pre-gate value, needed for dgate
-      float g[8], r[8];
-      const unsigned gb = static_cast<unsigned>(m) / static_cast<unsigned>(p.rows_per_gate);
-      load8(p.gate + static_cast<long long>(gb) * p.ld_gate + n, g);
-      load8(p.resid + m * p.ldr + n, r);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], g[j], r[j]);
+      if (!(p.debug & 4)) store8(p.aux + m * p.ld_aux + n, v);  // pre-gate value, needed for dgate
+      const uint4 gu = pf->g[pass], ru = pf->r[pass];
+      const float2 g0 = unpack_bf16x2(gu.x), g1 = unpack_bf16x2(gu.y), g2 = unpack_bf16x2(gu.z),
+                   g3 = unpack_bf16x2(gu.w);
+      const float2 r0 = unpack_bf16x2(ru.x), r1 = unpack_bf16x2(ru.y), r2 = unpack_bf16x2(ru.z),
+                   r3 = unpack_bf16x2(ru.w);
+      v[0] = fmaf(v[0], g0.x, r0.x); v[1] = fmaf(v[1], g0.y, r0.y);
+      v[2] = fmaf(v[2], g1.x, r1.x); v[3] = fmaf(v[3], g1.y, r1.y);
+      v[4] = fmaf(v[4], g2.x, r2.x); v[5] = fmaf(v[5], g2.y, r2.y);
+      v[6] = fmaf(v[6], g3.x, r3.x); v[7] = fmaf(v[7], g3.y, r3.y);
     }
     if constexpr (EV == EV_BF16 || EV == EV_BF16_BIAS || EV == EV_GATE) {
       store8(reinterpret_cast<bf16*>(p.D) + m * p.ldd + n, v);
@@ -316,6 +349,9 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
     for (int work = blockIdx.x; work < total_work; work += gridDim.x) {
       const int tile = work / p.split_k;
       const int m_blk = tile % p.tiles_m, n_blk = tile / p.tiles_m;
+      const long long m0 = static_cast<long long>(m_blk) * BLOCK_M + ew * 32;
+      [[maybe_unused]] GatePrefetch pf;
+      if constexpr (EV == EV_GATE) gate_prefetch(p, lane, m0, n_blk * block_n + (lane & 7) * 8, pf);
       mbar_wait(&tmem_full[as], aphase);
       tc_fence_after();
       // Accumulator rows live one per thread (TMEM lane).  Each 64-column chunk is transposed
@@ -326,6 +362,9 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
       const int nchunks = block_n / 64;
       const int sub_row = lane >> 3, seg = lane & 7;
       for (int c = 0; c < nchunks; ++c) {
+        if constexpr (EV == EV_GATE) {
+          if (c > 0) gate_prefetch(p, lane, m0, n_blk * block_n + c * 64 + seg * 8, pf);
+        }
         uint32_t r0[32], r1[32];
         if (!(p.debug & 2)) {
           tmem_ld32(taddr + c * 64, r0);
@@ -350,7 +389,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
         const int n = n_blk * block_n + c * 64 + seg * 8;
         if constexpr (EV != EV_GENERIC) {
           if (n < p.N && !(p.debug & 1))
-            epilogue_fast<EV>(p, wbuf, lane, static_cast<long long>(m_blk) * BLOCK_M + ew * 32, n);
+            epilogue_fast<EV>(p, wbuf, lane, m0, n, &pf);
         } else {
           const int nvalid = min(8, p.N - n);
 #pragma unroll 1
@@ -434,6 +473,14 @@ extern "C" int mmdit_gemm_bf16(const mmdit_gemm_args* a, void* stream_) {
   const int stage_bytes = A_STAGE_BYTES + p.block_n * BLOCK_K * 2;
   p.stages = (SMEM_BUDGET - 1024 - BAR_BYTES - EPI_STAGE_BYTES) / stage_bytes;
   if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
+  {
+    static int env_stages = -1;  // perf experiments: MMDIT_GEMM_STAGES caps the smem ring depth
+    if (env_stages < 0) {
+      const char* e = getenv("MMDIT_GEMM_STAGES");
+      env_stages = e ? atoi(e) : 0;
+    }
+    if (env_stages > 0 && p.stages > env_stages) p.stages = env_stages;
+  }
   p.tiles_m = (p.M + BLOCK_M - 1) / BLOCK_M;
   p.tiles_n = (p.N + p.block_n - 1) / p.block_n;
   p.kb_total = (p.K + BLOCK_K - 1) / BLOCK_K;
@@ -441,10 +488,17 @@ extern "C" int mmdit_gemm_bf16(const mmdit_gemm_args* a, void* stream_) {
   const int tiles = p.tiles_m * p.tiles_n;
   if (split <= 0) {
     split = 1;
-    if (a->accumulate && tiles < sms && p.kb_total >= 8) {
-      split = (sms + tiles - 1) / tiles;
-      if (split > p.kb_total / 4) split = p.kb_total / 4;
-      if (split < 1) split = 1;
+    if (a->accumulate && a->d_fp32 && p.kb_total >= 8) {
+      // model: time ~ waves * (k-blocks per unit + epilogue), epilogue ~ 10 k-block times
+      double best = 1e30;
+      const int max_split = p.kb_total / 4 > 0 ? p.kb_total / 4 : 1;
+      for (int s = 1; s <= max_split && s <= 64; ++s) {
+        const int per = (p.kb_total + s - 1) / s;
+        const long long units = (long long)tiles * ((p.kb_total + per - 1) / per);
+        const long long waves = (units + sms - 1) / sms;
+        const double t = (double)waves * (per + 10.0);
+        if (t < best - 1e-9) { best = t; split = s; }
+      }
     }
   }
   MMDIT_REQUIRE(split == 1 || (a->accumulate && a->d_fp32), MMDIT_ERR_ARG,
@@ -490,7 +544,7 @@ extern "C" int mmdit_gemm_bf16(const mmdit_gemm_args* a, void* stream_) {
                       (a->d_fp32 ? a->ldd % 4 == 0 : a->ldd % 8 == 0);
   const bool bias_ok = !a->bias || (a->bias_fp32 && al16(a->bias));
   int ev = EV_GENERIC;
-  if (vec_ok && !a->reserved) {
+  if (vec_ok) {
     if (a->d_fp32) {
       if (a->epilogue == MMDIT_EPI_NONE && !a->bias && !a->aux) {
         if (!a->accumulate) ev = EV_F32;

@@ -398,7 +398,7 @@ int mmdit_ln_modulate_bwd(const void* dy, const void* x, const float* mean, cons
   MMDIT_REQUIRE(dy && x && mean && rstd && scale && dx && dshift && dscale && rows > 0 &&
                     d % 8 == 0 && rows_per_batch > 0 && rows % rows_per_batch == 0,
                 MMDIT_ERR_ARG, "ln_modulate_bwd: bad arguments");
-  const int rpb = 32;
+  const int rpb = 16;  // 2 rows per warp: >2 waves of blocks at cfg2 sizes, few atomics
   const int bpb = (int)((rows_per_batch + rpb - 1) / rpb);
   const unsigned grid = (unsigned)((rows / rows_per_batch) * bpb);
   const size_t smem = 2 * (size_t)d * sizeof(float);
@@ -415,7 +415,7 @@ int mmdit_gate_bwd(const void* dout, const void* a, const void* gate, void* da, 
   MMDIT_REQUIRE(dout && a && gate && da && dgate && rows > 0 && d % 8 == 0 && rows_per_batch > 0 &&
                     rows % rows_per_batch == 0,
                 MMDIT_ERR_ARG, "gate_bwd: bad arguments");
-  const int rpb = 32;
+  const int rpb = 16;  // 2 rows per warp: >2 waves of blocks at cfg2 sizes, few atomics
   const int bpb = (int)((rows_per_batch + rpb - 1) / rpb);
   const unsigned grid = (unsigned)((rows / rows_per_batch) * bpb);
   const size_t smem = 2 * (size_t)d * sizeof(float);

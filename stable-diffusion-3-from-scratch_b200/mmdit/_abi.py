@@ -15,6 +15,7 @@ SIGNATURES = {
     "mmdit_attn_bwd": [vp, vp],
     "mmdit_ln_modulate_fwd": [vp, vp, vp, vp, vp, vp, i64, i32, i64, i64, f32, vp],
     "mmdit_ln_modulate_bwd": [vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, i64, i64, i64, vp],
+    "mmdit_gate_residual_fwd": [vp, vp, vp, vp, i64, i32, i64, i64, vp],
     "mmdit_gate_bwd": [vp, vp, vp, vp, vp, vp, i64, i32, i64, i64, i64, i64, vp],
     "mmdit_text_norm_fwd": [vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, f32, vp],
     "mmdit_text_norm_bwd": [vp, vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, i32, vp],

@@ -7,11 +7,17 @@ torch.optim / GradScaler / clip_grad_norm_ / DDP keep working unchanged.
 Backward math follows SURVEY App. E (restated from the reference forward; the
 reference itself relies on autograd).
 """
+import os
+
 import torch
 from torch.autograd import Function
 
 from . import ops
 from .ops import BF16, F32
+
+
+# MMDIT_FUSED_GATE=1 routes gate*x+residual through the GEMM epilogue instead of a separate kernel
+FUSED_GATE_EPILOGUE = os.environ.get("MMDIT_FUSED_GATE", "0") == "1"
 
 
 def _split_rows(t, sizes):
@@ -70,9 +76,15 @@ class GatedLinearFn(Function):
     @staticmethod
     def forward(ctx, a, wb, bb, gate, resid, rows_per_batch, w, b):
         R = a.shape[0]
-        aux = torch.empty((R, wb.shape[0]), device=a.device, dtype=BF16)
-        o = ops.gemm(a, wb, bias=bb, epilogue=ops.EPI_GATE_RESID, gate=gate,
-                     rows_per_gate=rows_per_batch, resid=resid, aux=aux)
+        if FUSED_GATE_EPILOGUE:
+            aux = torch.empty((R, wb.shape[0]), device=a.device, dtype=BF16)
+            o = ops.gemm(a, wb, bias=bb, epilogue=ops.EPI_GATE_RESID, gate=gate,
+                         rows_per_gate=rows_per_batch, resid=resid, aux=aux)
+        else:
+            # measured on B200 (profiles/): the plain-epilogue GEMM plus one streaming pass beats the
+            # fused gate+residual epilogue, whose dependent global loads stall the 4 epilogue warps
+            aux = ops.gemm(a, wb, bias=bb)
+            o = ops.gate_residual_fwd(aux, gate, resid, rows_per_batch)
         ctx.save_for_backward(a, wb, aux, gate)
         ctx.rpb = rows_per_batch
         ctx.has_bias = b is not None

@@ -54,6 +54,17 @@ def gemm(A, B, *, a_major=0, b_major=0, out=None, out_dtype=BF16, accumulate=Fal
     N, Kb = (B.shape[1], B.shape[0]) if b_major else (B.shape[0], B.shape[1])
     if K != Kb:
         raise ValueError(f"gemm: reduction dims differ ({K} vs {Kb})")
+    if (out is None and out_dtype == BF16 and M <= 128 and K >= 2048 and epilogue == EPI_NONE
+            and bias is None and aux is None and remap is None and not simt):
+        # few output tiles, long reduction (adaLN dgrads with M = batch): split-K over all SMs
+        # into an fp32 buffer, then one cast
+        acc = gemm(A, B, a_major=a_major, b_major=b_major, out_dtype=F32, accumulate=True)
+        return acc.to(BF16)
+    if out is None and out_dtype == F32 and not accumulate and remap is None and epilogue == EPI_NONE:
+        # wgrad-style outputs: few tiles, long reduction -> zero-init and let split-K atomics fill all SMs
+        if ((M + 127) // 128) * ((N + 255) // 256) < 120 and K >= 1024:
+            out = torch.zeros((M, N), device=A.device, dtype=F32)
+            accumulate = True
     if out is None:
         rows = out_rows if out_rows is not None else M
         if remap is not None and out_rows is None:
@@ -329,4 +340,15 @@ def cast_bf16(x, out=None):
         out = torch.empty(x.shape, device=x.device, dtype=BF16)
     _lib.check(_lib.lib().mmdit_cast_f32_bf16(_p(x), _p(out), x.numel(), _s()),
                "mmdit_cast_f32_bf16")
+    return out
+
+
+def gate_residual_fwd(a, gate, resid, rows_per_batch):
+    """out = a * gate[row // rows_per_batch] + resid (all bf16, a/resid [R,d] contiguous)."""
+    R, d = a.shape
+    assert a.is_contiguous() and resid.is_contiguous()
+    out = torch.empty_like(a)
+    _lib.check(_lib.lib().mmdit_gate_residual_fwd(_p(a), _p(gate), _p(resid), _p(out), R, d,
+                                                  rows_per_batch, gate.stride(0), _s()),
+               "mmdit_gate_residual_fwd")
     return out

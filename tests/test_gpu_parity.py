@@ -89,10 +89,7 @@ def test_model_forward_backward_vs_oracle_and_golden(dev, golden, name):
             assert float(p.grad.abs().max()) == 0.0, k        # dead text queries of the last block
             continue
         err = float((p.grad - go).abs().max()) / den
-        floor = 0.0
-        if k in g["grads_bf16"]:
-            rb, rf = g["grads_bf16"][k], g["grads_fp32"][k]
-            floor = float((rb - rf).abs().max() / rf.abs().max())
+        floor = g["grad_relerr_bf16"].get(k, 0.0)   # the reference's own bf16-autocast error on this tensor
         assert err <= max(4e-2, 3 * floor), (k, err, floor)
         n, n_ref = float(p.grad.norm()), g["gradnorm_fp32"][k]
         assert abs(n - n_ref) <= max(4e-2, 3 * floor) * n_ref + 1e-7, (k, n, n_ref)

@@ -37,6 +37,12 @@ struct AttnBwdParams {
   float scale, scale_log2;
 };
 
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c),
                "f"(d)
@@ -113,7 +119,6 @@ attn_bwd_kernel(const __grid_constant__ AttnBwdParams p) {
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t id_kk = make_idesc_bf16(128, 128, 0, 0);  // S^T, dP^T
       const uint32_t id_kn = make_idesc_bf16(128, 64, 0, 1);   // dV, dK
       const uint32_t id_nn = make_idesc_bf16(128, 64, 1, 1);   // dQ
       const uint32_t k_addr = smem_u32(sK), v_addr = smem_u32(sV);
@@ -123,23 +128,25 @@ attn_bwd_kernel(const __grid_constant__ AttnBwdParams p) {
         const int st = i & 1;
         const uint32_t q_addr = smem_u32(sQ + st * ATT_TILE_BYTES);
         const uint32_t do_addr = smem_u32(sdO + st * ATT_TILE_BYTES);
+        const int qs = i < ntx ? 0 : 1;
+        const int row0 = (qs == 0 ? i : i - ntx) * ATT_TILE;
+        const int nq = (min(ATT_TILE, (qs == 0 ? p.N : p.M) - row0) + 15) & ~15;  // queries that exist
+        const uint32_t id_kq = make_idesc_bf16(128, nq, 0, 0);
         mbar_wait(&qdo_full[st], (i >> 1) & 1);
         tc_fence_after();
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          umma_bf16(tm_St, desc_kmajor(k_addr, k), desc_kmajor(q_addr, k), id_kk, k > 0);
+          umma_bf16(tm_St, desc_kmajor(k_addr, k), desc_kmajor(q_addr, k), id_kq, k > 0);
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          umma_bf16(tm_dPt, desc_kmajor(v_addr, k), desc_kmajor(do_addr, k), id_kk, k > 0);
+          umma_bf16(tm_dPt, desc_kmajor(v_addr, k), desc_kmajor(do_addr, k), id_kq, k > 0);
         umma_commit(st_full);
         mbar_wait(pt_full, i & 1);
         tc_fence_after();
-#pragma unroll
-        for (int k = 0; k < 8; ++k)
+        for (int k = 0; k < nq / 16; ++k)
           umma_bf16(tm_dV, desc_kmajor(pt_addr + (k >> 2) * ATT_TILE_BYTES, k & 3),
                     desc_mnmajor(do_addr, k, ATT_TILE_BYTES), id_kn, (i > 0 || k > 0) ? 1u : 0u);
-#pragma unroll
-        for (int k = 0; k < 8; ++k)
+        for (int k = 0; k < nq / 16; ++k)
           umma_bf16(tm_dK, desc_kmajor(dst_addr + (k >> 2) * ATT_TILE_BYTES, k & 3),
                     desc_mnmajor(q_addr, k, ATT_TILE_BYTES), id_kn, (i > 0 || k > 0) ? 1u : 0u);
         if (i > 0) {
@@ -181,8 +188,10 @@ attn_bwd_kernel(const __grid_constant__ AttnBwdParams p) {
       mbar_wait(st_full, i & 1);
       tc_fence_after();
       if (i > 0) mbar_wait(dq_full, (i - 1) & 1);  // MMAs of tile i-1 no longer read sPt/sdSt
+      const int nq = (q_valid + 15) & ~15;
 #pragma unroll 1
       for (int c = 0; c < 2; ++c) {
+        if (hf * 64 + c * 32 >= nq) break;  // warp-uniform: these query columns do not exist
         uint32_t s[32], dp[32];
         tmem_ld32(tm_St + lane_off + hf * 64 + c * 32, s);
         tmem_ld32(tm_dPt + lane_off + hf * 64 + c * 32, dp);
@@ -196,7 +205,7 @@ attn_bwd_kernel(const __grid_constant__ AttnBwdParams p) {
           for (int j = 0; j < 8; ++j) {
             const int col = hf * 64 + c * 32 + g * 8 + j;
             const float pv =
-                k_ok ? exp2f(fmaf(__uint_as_float(s[g * 8 + j]), sl2, -lse_s[col])) : 0.f;
+                k_ok ? ex2_approx(fmaf(__uint_as_float(s[g * 8 + j]), sl2, -lse_s[col])) : 0.f;
             pe[j] = pv;
             de[j] = pv * (__uint_as_float(dp[g * 8 + j]) - del_s[col]) * p.scale;
           }

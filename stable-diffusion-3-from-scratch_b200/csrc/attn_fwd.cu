@@ -26,6 +26,12 @@ constexpr int ATT_THREADS = 192;
 constexpr int ATT_TILE_BYTES = ATT_TILE * ATT_HD * 2;  // 16 KiB
 constexpr int ATT_SMEM = 7 * ATT_TILE_BYTES + 256;     // Q, K[2], V[2], P(2 tiles) + barriers
 
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 struct AttnFwdParams {
   CUtensorMap tmQ[2], tmK[2], tmV[2];  // [0] image stream, [1] text stream
   bf16* o[2];
@@ -71,6 +77,12 @@ attn_fwd_kernel(const __grid_constant__ AttnFwdParams p) {
     mbar_fence_init();
   }
   if (warp == 0) {
+    if (lane == 0) {
+      tma_prefetch_desc(&p.tmQ[qs]);
+      tma_prefetch_desc(&p.tmK[0]);
+      tma_prefetch_desc(&p.tmV[0]);
+      if (ntc > 0) { tma_prefetch_desc(&p.tmK[1]); tma_prefetch_desc(&p.tmV[1]); }
+    }
     tmem_alloc(tmem_slot, 256);
     tmem_relinquish();
   }
@@ -96,12 +108,16 @@ attn_fwd_kernel(const __grid_constant__ AttnFwdParams p) {
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
       const uint32_t idesc_o = make_idesc_bf16(128, 64, 0, 1);
       const uint32_t q_addr = smem_u32(sQ), p_addr = smem_u32(sP);
       mbar_wait(q_full, 0);
       for (int j = 0; j < nkv; ++j) {
         const int st = j & 1;
+        const int ks = j < ntx ? 0 : 1;
+        const int row0 = (ks == 0 ? j : j - ntx) * ATT_TILE;
+        const int nv = min(ATT_TILE, (ks == 0 ? p.N : p.M) - row0);
+        const int n_mma = (nv + 15) & ~15;  // partial key tiles: only the columns that exist
+        const uint32_t idesc_s = make_idesc_bf16(128, n_mma, 0, 0);
         const uint32_t k_addr = smem_u32(sK + st * ATT_TILE_BYTES);
         const uint32_t v_addr = smem_u32(sV + st * ATT_TILE_BYTES);
         mbar_wait(&kv_full[st], (j >> 1) & 1);
@@ -112,8 +128,7 @@ attn_fwd_kernel(const __grid_constant__ AttnFwdParams p) {
         umma_commit(s_full);
         mbar_wait(p_full, j & 1);
         tc_fence_after();
-#pragma unroll
-        for (int k = 0; k < ATT_TILE / 16; ++k)
+        for (int k = 0; k < n_mma / 16; ++k)
           umma_bf16(tmem_O, desc_kmajor(p_addr + (k >> 2) * ATT_TILE_BYTES, k & 3),
                     desc_mnmajor(v_addr, k, ATT_TILE_BYTES), idesc_o, (j > 0 || k > 0) ? 1u : 0u);
         umma_commit(&kv_empty[st]);
@@ -131,43 +146,53 @@ attn_fwd_kernel(const __grid_constant__ AttnFwdParams p) {
       const int ks = j < ntx ? 0 : 1;
       const int row0 = (ks == 0 ? j : j - ntx) * ATT_TILE;
       const int nv = min(ATT_TILE, (ks == 0 ? p.N : p.M) - row0);  // valid keys in this tile
-      const int nchunk = (nv + 31) / 32;
+      const int n_mma = (nv + 15) & ~15;
+      const int nchunk = (n_mma + 31) / 32;
       mbar_wait(s_full, j & 1);
       tc_fence_after();
-      float mx = -INFINITY;
-      for (int c = 0; c < nchunk; ++c) {
-        uint32_t s[32];
-        tmem_ld32(tmem_S + lane_off + c * 32, s);
+      // pass 1: row maximum (4 independent chains; TMEM loads issued in pairs)
+      float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+      for (int c = 0; c < nchunk; c += 2) {
+        uint32_t s0[32], s1[32];
+        tmem_ld32(tmem_S + lane_off + c * 32, s0);
+        if (c + 1 < nchunk) tmem_ld32(tmem_S + lane_off + (c + 1) * 32, s1);
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 32; ++i)
-          if (c * 32 + i < nv) mx = fmaxf(mx, __uint_as_float(s[i]));
+          if (c * 32 + i < nv) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(s0[i]));
+        if (c + 1 < nchunk) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if ((c + 1) * 32 + i < nv) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(s1[i]));
+        }
       }
+      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
       const float m_new = fmaxf(m, mx);
-      const float alpha = exp2f((m - m_new) * sl2);
+      const float alpha = ex2_approx((m - m_new) * sl2);
       const float mb = m_new * sl2;
       if (j > 0) {
         mbar_wait(pv_done, (j - 1) & 1);
         tc_fence_after();
+        // rescale O only if some row of this warp actually raised its maximum
+        if (!__all_sync(0xffffffffu, m_new == m)) {
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          uint32_t o[32];
-          tmem_ld32(tmem_O + lane_off + c * 32, o);
-          tmem_ld_wait();
+          for (int c = 0; c < 2; ++c) {
+            uint32_t o[32];
+            tmem_ld32(tmem_O + lane_off + c * 32, o);
+            tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-          tmem_st32(tmem_O + lane_off + c * 32, o);
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st32(tmem_O + lane_off + c * 32, o);
+          }
+          tmem_st_wait();
         }
-        tmem_st_wait();
       }
-      float rs = 0.f;
+      float rs4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < nchunk; ++c) {
         uint32_t s[32];
-        if (c < nchunk) {
-          tmem_ld32(tmem_S + lane_off + c * 32, s);
-          tmem_ld_wait();
-        }
+        tmem_ld32(tmem_S + lane_off + c * 32, s);
+        tmem_ld_wait();
         uint8_t* prow = sP + (c >> 1) * ATT_TILE_BYTES + r * 128;
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
@@ -175,9 +200,8 @@ attn_fwd_kernel(const __grid_constant__ AttnFwdParams p) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int col = c * 32 + g * 8 + i;
-            e[i] = (c < nchunk && col < nv) ? exp2f(fmaf(__uint_as_float(s[g * 8 + i]), sl2, -mb))
-                                            : 0.f;
-            rs += e[i];
+            e[i] = col < nv ? ex2_approx(fmaf(__uint_as_float(s[g * 8 + i]), sl2, -mb)) : 0.f;
+            rs4[i & 3] += e[i];
           }
           uint4 u;
           u.x = pack_bf16x2(e[0], e[1]); u.y = pack_bf16x2(e[2], e[3]);
@@ -186,6 +210,7 @@ attn_fwd_kernel(const __grid_constant__ AttnFwdParams p) {
           *reinterpret_cast<uint4*>(prow + ((chunk16 ^ (r & 7)) << 4)) = u;
         }
       }
+      const float rs = (rs4[0] + rs4[1]) + (rs4[2] + rs4[3]);
       l = l * alpha + rs;
       m = m_new;
       fence_proxy_async_smem();

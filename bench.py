@@ -251,17 +251,22 @@ def run_product(args):
     ms_e2e = timed_loop(e2e_step, args.steps)
     e2e_value = world * BATCH * args.steps / (ms_e2e / 1e3)
 
+    # ---- per-kernel-class roofline from an instrumented, untimed step (eager, same shapes).
+    # Runs on EVERY rank: with data parallelism the backward launches gradient all-reduces.
+    probe = RFTrainer(model, world_size=1, use_graph=False) if trainer.use_graph else trainer
+    probe._zero(); probe._fwd_bwd(fresh(1)); probe._update()     # eager warm-up of the probe path
+    c1 = _lib.launch_count()
+    kern = instrument_kernels(probe, fresh(0))
+    launches_per_step = _lib.launch_count() - c1
+    if world > 1:
+        probe._update()
+    barrier()
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
-
-    # ---- per-kernel-class roofline from an instrumented, untimed step (eager, same shapes)
     pk = peaks()
-    probe = RFTrainer(model, world_size=1, use_graph=False) if trainer.use_graph else trainer
-    c1 = _lib.launch_count()
-    kern = instrument_kernels(probe, fresh(0))
-    launches_per_step = _lib.launch_count() - c1
     f_img, f_attn_img = train_flops_per_image(CFG2, (LATENT // 2) ** 2, TEXT_TOKENS)
     g = kern["gemm"]
     gemm_tf = g["flops"] / (g["ms"] * 1e-3) / 1e12 if g["ms"] else 0.0

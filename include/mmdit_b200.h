@@ -204,6 +204,23 @@ int mmdit_fold_rows_f32(const float* in, float* out, int32_t rows, int32_t n, in
                         void* stream);
 int mmdit_cast_f32_bf16(const float* in, void* out, int64_t n, void* stream);
 
+/* ---------------------------------------------------------- optimizer step --
+ * Fused gradient-norm clip + AdamW + bf16 shadow refresh over many tensors
+ * (model_trainer.py:483-503; "next" row (f)-1 of the scope table).  table: device array of
+ * mmdit_param_desc; chunks: device array of int32 pairs (tensor index, chunk index) with
+ * mmdit_adamw_chunk_elems() elements per chunk; state: device float[2] = {grad sum of squares,
+ * step count}, owned by the caller and persistent across steps (the step count is incremented
+ * on the device, so the call is CUDA-graph replayable).  max_norm <= 0 disables clipping. */
+typedef struct mmdit_param_desc {
+  float* p; const float* g; float* m; float* v;
+  void* shadow;          /* bf16 copy of p refreshed in the same pass, or NULL */
+  int64_t n;
+} mmdit_param_desc;
+int mmdit_adamw_step(const void* table, const void* chunks, int32_t n_chunks, float* state,
+                     float lr, float beta1, float beta2, float eps, float weight_decay,
+                     float max_norm, void* stream);
+int mmdit_adamw_chunk_elems(void);
+
 #ifdef __cplusplus
 }
 #endif

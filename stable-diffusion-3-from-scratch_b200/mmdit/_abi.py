@@ -34,4 +34,6 @@ SIGNATURES = {
     "mmdit_colsum_bf16": [vp, vp, i64, i32, i64, vp],
     "mmdit_fold_rows_f32": [vp, vp, i32, i32, i64, vp],
     "mmdit_cast_f32_bf16": [vp, vp, i64, vp],
+    "mmdit_adamw_step": [vp, vp, i32, vp, f32, f32, f32, f32, f32, f32, vp],
+    "mmdit_adamw_chunk_elems": [],
 }

@@ -15,6 +15,7 @@ import torch.distributed as dist
 
 from . import ops
 from .functional import rf_loss
+from .optim import FusedAdamW
 
 BF16, F32 = torch.bfloat16, torch.float32
 
@@ -118,7 +119,7 @@ class GradBuckets:
 
 class RFTrainer:
     def __init__(self, model, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01, clip=1.0,
-                 world_size=1, process_group=None, use_graph=False):
+                 world_size=1, process_group=None, use_graph=False, fused_optimizer=True):
         self.model = model
         self.device = next(model.parameters()).device
         self.clip = clip
@@ -129,8 +130,14 @@ class RFTrainer:
                                    self.device) if world_size > 1 else None
         if self.buckets is not None:
             self.buckets.install_hooks()
-        self.opt = torch.optim.AdamW(self.params, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay,
-                                     fused=True, capturable=self.use_graph)
+        self.fused_optimizer = fused_optimizer
+        if fused_optimizer:
+            # clip + AdamW + bf16 shadow refresh in two kernels (mmdit/optim.py)
+            self.opt = FusedAdamW(model, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, max_norm=clip)
+        else:
+            self.opt = torch.optim.AdamW(self.params, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay,
+                                         fused=True, capturable=self.use_graph)
+        self._bound = False
         self.graph = None
         self.static = None
         self.loss = None
@@ -156,8 +163,14 @@ class RFTrainer:
     def _update(self):
         if self.buckets is not None:
             self.buckets.finish()
-        torch.nn.utils.clip_grad_norm_(self.params, self.clip)       # :487
-        self.opt.step()                                               # :491
+        if self.fused_optimizer:
+            if not self._bound:        # the first forward has built the bf16 shadow buffers
+                self.opt.bind_shadows()
+                self._bound = True
+            self.opt.step()                                           # :483-491 in one pass
+        else:
+            torch.nn.utils.clip_grad_norm_(self.params, self.clip)   # :487
+            self.opt.step()                                           # :491
 
     def _zero(self):
         if self.buckets is not None:

@@ -163,3 +163,31 @@ def test_euler_cfg_sampler_vs_oracle(dev):
     mse = float(((out - ref) ** 2).mean())
     psnr = 10 * torch.log10(torch.tensor(4.0 / max(mse, 1e-12)))     # peak-to-peak 2 -> 4 = 2^2
     assert float(psnr) >= 30.0, float(psnr)
+
+
+def test_fused_adamw_matches_torch_adamw_and_refreshes_shadows(dev):
+    """Fused clip+AdamW+shadow kernel vs torch clip_grad_norm_ + torch.optim.AdamW on the same grads."""
+    from mmdit.optim import FusedAdamW
+    from mmdit.shadow import packed_weight
+    torch.manual_seed(0)
+    lin = torch.nn.Sequential(torch.nn.Linear(96, 200), torch.nn.Linear(200, 33)).to(dev)
+    ref = torch.nn.Sequential(torch.nn.Linear(96, 200), torch.nn.Linear(200, 33)).to(dev)
+    ref.load_state_dict(lin.state_dict())
+    wb = packed_weight(lin[0], "w", [lin[0].weight])
+    opt = FusedAdamW(lin, lr=1e-2, max_norm=1.0)
+    opt.bind_shadows()
+    topt = torch.optim.AdamW(ref.parameters(), lr=1e-2, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01)
+    for step in range(5):
+        x = torch.randn(64, 96, device=dev)
+        for net in (lin, ref):
+            for p in net.parameters():
+                p.grad = None
+            (net(x) ** 2).mean().mul(50).backward()
+        n_ref = torch.nn.utils.clip_grad_norm_(ref.parameters(), 1.0)
+        topt.step()
+        opt.step()
+        assert abs(float(opt.grad_norm()) - float(n_ref)) <= 1e-4 * float(n_ref)
+    for a, b in zip(lin.parameters(), ref.parameters()):
+        assert float((a - b).abs().max()) <= 2e-6 + 1e-5 * float(b.abs().max())
+    assert torch.equal(packed_weight(lin[0], "w", [lin[0].weight]), lin[0].weight.detach().bfloat16())
+    assert packed_weight(lin[0], "w", [lin[0].weight]).data_ptr() == wb.data_ptr()

@@ -122,25 +122,29 @@ int mmdit_attn_bwd(const mmdit_attn_args* args, void* stream);
  * y = LN(x) * (1 + scale[b]) + shift[b], LN eps, no affine (Norm.py:16-23).
  * shift/scale: bf16 [B, d] with row stride ld_mod; b = row / rows_per_batch.
  * bwd: dx = LN-backward(dy * (1+scale)) (+ dres), dshift/dscale (fp32, row
- * stride ld_dmod) are ACCUMULATED with atomics -- zero them first. */
+ * stride ld_dmod) are WRITTEN (two-stage reduction through `workspace`). */
 int mmdit_ln_modulate_fwd(const void* x, const void* shift, const void* scale, void* y, float* mean,
                           float* rstd, int64_t rows, int32_t d, int64_t rows_per_batch,
                           int64_t ld_mod, float eps, void* stream);
 int mmdit_ln_modulate_bwd(const void* dy, const void* x, const float* mean, const float* rstd,
                           const void* scale, const void* dres, void* dx, float* dshift,
-                          float* dscale, int64_t rows, int32_t d, int64_t rows_per_batch,
-                          int64_t ld_mod, int64_t ld_dmod, void* stream);
+                          float* dscale, float* workspace, int64_t rows, int32_t d,
+                          int64_t rows_per_batch, int64_t ld_mod, int64_t ld_dmod, void* stream);
+/* fp32 elements of `workspace` needed by ln_modulate_bwd / gate_bwd (per-block partial sums;
+ * the column reductions are two-stage, no atomics). */
+int64_t mmdit_rowreduce_workspace_floats(int64_t rows, int32_t d, int64_t rows_per_batch);
 
 /* Backward of the gated residual o = a * gate[b] + x (Transformer_Block_Dual.py:64-76):
  * da = dout * gate[b]; dgate[b] += sum_rows dout * a; dab[b] += sum_rows da (optional,
- * per-sample partial of the bias gradient of the producing linear). fp32 outputs accumulate. */
+ * per-sample partial of the bias gradient of the producing linear). fp32 outputs are written;
+ * workspace: mmdit_rowreduce_workspace_floats(rows, d, rows_per_batch) floats. */
 /* Forward of the same gated residual as a standalone kernel: out = a * gate[b] + resid. */
 int mmdit_gate_residual_fwd(const void* a, const void* gate, const void* resid, void* out,
                             int64_t rows, int32_t d, int64_t rows_per_batch, int64_t ld_gate,
                             void* stream);
 int mmdit_gate_bwd(const void* dout, const void* a, const void* gate, void* da, float* dgate,
-                   float* dab, int64_t rows, int32_t d, int64_t rows_per_batch, int64_t ld_gate,
-                   int64_t ld_dgate, int64_t ld_dab, void* stream);
+                   float* dab, float* workspace, int64_t rows, int32_t d, int64_t rows_per_batch,
+                   int64_t ld_gate, int64_t ld_dgate, int64_t ld_dab, void* stream);
 
 /* Text front-end (diff_model.py:168-172,323-326): out = bf16(sigma * RMSNorm_fp32(c) * w).
  * Tokens [0,split) of each sample use (w1,sigma1) -> out1 [B*split, d]; tokens [split,M)
@@ -166,10 +170,11 @@ int mmdit_qknorm_rope_bwd(const void* dqk, const void* qkv, const float* wq, con
                           int64_t ld_dout, int32_t tokens_per_sample, float eps, void* stream);
 
 /* SwiGLU activation, xformers semantics (MLP.py:19,32): h12 = [x1 | x2], a = silu(x1) * x2.
- * bwd writes dh12 and accumulates db12 [2*hidden] (may be NULL). */
+ * bwd writes dh12 and adds the column sums to db12 [2*hidden] (may be NULL; else needs workspace). */
 int mmdit_swiglu_fwd(const void* h12, void* a, int64_t rows, int32_t hidden, void* stream);
-int mmdit_swiglu_bwd(const void* da, const void* h12, void* dh12, float* db12, int64_t rows,
-                     int32_t hidden, void* stream);
+int mmdit_swiglu_bwd(const void* da, const void* h12, void* dh12, float* db12, float* workspace,
+                     int64_t rows, int32_t hidden, void* stream);
+int64_t mmdit_swiglu_bwd_workspace_floats(int64_t rows, int32_t hidden);
 
 /* Timestep embedding (PositionalEncoding.py:23-30 with t * time_scale, diff_model.py:306):
  * out bf16 [B, d]; denom fp32 [d] as built by the reference ctor. bwd accumulates dscale[1]. */

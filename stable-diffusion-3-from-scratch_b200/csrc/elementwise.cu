@@ -212,7 +212,7 @@ swiglu_fwd_kernel(const bf16* __restrict__ h12, bf16* __restrict__ a, long long 
 // Block = 128 threads x 8 columns = 1024 hidden columns, strip of rows_per_block rows.
 __global__ void __launch_bounds__(128)
 swiglu_bwd_kernel(const bf16* __restrict__ da, const bf16* __restrict__ h12,
-                  bf16* __restrict__ dh12, float* __restrict__ db12, long long R, int hid,
+                  bf16* __restrict__ dh12, float* __restrict__ partial, long long R, int hid,
                   int rows_per_block) {
   const int col = (blockIdx.x * 128 + threadIdx.x) * 8;
   if (col >= hid) return;
@@ -239,12 +239,12 @@ swiglu_bwd_kernel(const bf16* __restrict__ da, const bf16* __restrict__ h12,
     store8(dh12 + row * 2 * hid + col, d1);
     store8(dh12 + row * 2 * hid + hid + col, d2);
   }
-  if (db12) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      atomicAdd(db12 + col + j, b1[j]);
-      atomicAdd(db12 + hid + col + j, b2[j]);
-    }
+  if (partial) {  // one fp32 row of column sums per row strip; folded by fold_rows_f32_kernel
+    float* dst = partial + (long long)blockIdx.y * 2 * hid;
+    *reinterpret_cast<float4*>(dst + col) = make_float4(b1[0], b1[1], b1[2], b1[3]);
+    *reinterpret_cast<float4*>(dst + col + 4) = make_float4(b1[4], b1[5], b1[6], b1[7]);
+    *reinterpret_cast<float4*>(dst + hid + col) = make_float4(b2[0], b2[1], b2[2], b2[3]);
+    *reinterpret_cast<float4*>(dst + hid + col + 4) = make_float4(b2[4], b2[5], b2[6], b2[7]);
   }
 }
 
@@ -510,15 +510,25 @@ int mmdit_swiglu_fwd(const void* h12, void* a, int64_t rows, int32_t hidden, voi
   return check_launch("swiglu_fwd_kernel");
 }
 
-int mmdit_swiglu_bwd(const void* da, const void* h12, void* dh12, float* db12, int64_t rows,
-                     int32_t hidden, void* stream) {
-  MMDIT_REQUIRE(da && h12 && dh12 && rows > 0 && hidden > 0 && hidden % 8 == 0, MMDIT_ERR_ARG,
-                "swiglu_bwd: bad arguments");
+int64_t mmdit_swiglu_bwd_workspace_floats(int64_t rows, int32_t hidden) {
+  return rows > 0 && hidden > 0 ? ((rows + 63) / 64) * 2 * (int64_t)hidden : 0;
+}
+
+int mmdit_swiglu_bwd(const void* da, const void* h12, void* dh12, float* db12, float* workspace,
+                     int64_t rows, int32_t hidden, void* stream) {
+  MMDIT_REQUIRE(da && h12 && dh12 && rows > 0 && hidden > 0 && hidden % 8 == 0 &&
+                    (!db12 || workspace),
+                MMDIT_ERR_ARG, "swiglu_bwd: bad arguments (db12 needs a workspace)");
   const int rpb = 64;
-  dim3 grid((unsigned)((hidden / 8 + 127) / 128), (unsigned)((rows + rpb - 1) / rpb));
+  const int nrb = (int)((rows + rpb - 1) / rpb);
+  dim3 grid((unsigned)((hidden / 8 + 127) / 128), (unsigned)nrb);
   swiglu_bwd_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>((const bf16*)da, (const bf16*)h12,
-                                                           (bf16*)dh12, db12, rows, hidden, rpb);
-  return check_launch("swiglu_bwd_kernel");
+                                                           (bf16*)dh12, db12 ? workspace : nullptr,
+                                                           rows, hidden, rpb);
+  if (db12)
+    fold_rows_f32_kernel<<<(2 * hidden + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+        workspace, db12, nrb, 2 * hidden, 2 * (long long)hidden);
+  return check_launch("swiglu_bwd_kernel", db12 ? 2 : 1);
 }
 
 int mmdit_timestep_embed_fwd(const float* t, const float* time_scale, const float* denom, void* out,

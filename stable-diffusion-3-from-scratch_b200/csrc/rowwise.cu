@@ -16,6 +16,50 @@ namespace mmdit {
 constexpr int ROW_THREADS = 256;
 constexpr int ROW_WARPS = ROW_THREADS / 32;
 
+// Column reductions of the backward kernels: no atomics.  Each warp keeps per-lane column
+// partials in registers; the block folds its warps through shared memory and writes one
+// [2][d] partial; a second tiny kernel folds the partials of each sample.
+constexpr int BWD_THREADS = 128;
+constexpr int BWD_WARPS = BWD_THREADS / 32;
+
+template <int NC>
+__device__ __forceinline__ void block_fold_partials(float* red, const float (&a0)[NC][8],
+                                                    const float (&a1)[NC][8], float* out, int d,
+                                                    int warp, int lane) {
+  float* mine = red + (long long)warp * 2 * d;
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    const int col = c * 256 + lane * 8;
+    if (col < d) {
+      *reinterpret_cast<float4*>(mine + col) = make_float4(a0[c][0], a0[c][1], a0[c][2], a0[c][3]);
+      *reinterpret_cast<float4*>(mine + col + 4) = make_float4(a0[c][4], a0[c][5], a0[c][6], a0[c][7]);
+      *reinterpret_cast<float4*>(mine + d + col) = make_float4(a1[c][0], a1[c][1], a1[c][2], a1[c][3]);
+      *reinterpret_cast<float4*>(mine + d + col + 4) = make_float4(a1[c][4], a1[c][5], a1[c][6], a1[c][7]);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * d; i += BWD_THREADS) {
+    float acc = 0.f;
+#pragma unroll
+    for (int w = 0; w < BWD_WARPS; ++w) acc += red[(long long)w * 2 * d + i];
+    out[i] = acc;
+  }
+}
+
+// out0[b, col] = sum_k partial[b, k, 0, col]; out1[b, col] = sum_k partial[b, k, 1, col]
+__global__ void fold_batch_partials_kernel(const float* __restrict__ partial, float* __restrict__ out0,
+                                           float* __restrict__ out1, int d, int blocks_per_batch,
+                                           long long ld0, long long ld1) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // 0 .. 2d
+  if (i >= 2 * d) return;
+  const long long b = blockIdx.y;
+  const float* src = partial + b * blocks_per_batch * 2 * d + i;
+  float acc = 0.f;
+  for (int k = 0; k < blocks_per_batch; ++k) acc += src[(long long)k * 2 * d];
+  if (i < d) out0[b * ld0 + i] = acc;
+  else if (out1) out1[b * ld1 + (i - d)] = acc;
+}
+
 template <int NC>
 __device__ __forceinline__ void load_row(const bf16* p, int d, int lane, float (&v)[NC][8]) {
 #pragma unroll
@@ -90,14 +134,14 @@ ln_mod_fwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ shift,
 // g = dy*(1+s); dx = rstd*(g - mean(g) - xhat*mean(g*xhat)) (+ dres)
 // dshift[b] += sum_rows dy ; dscale[b] += sum_rows dy*xhat      (fp32 atomics)
 template <int NC>
-__global__ void __launch_bounds__(ROW_THREADS)
+__global__ void __launch_bounds__(BWD_THREADS)
 ln_mod_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
                   const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
                   const bf16* __restrict__ scale, const bf16* __restrict__ dres,
-                  bf16* __restrict__ dx, float* __restrict__ dshift, float* __restrict__ dscale,
-                  int d, long long rows_per_batch, long long ld_mod, long long ld_dmod,
+                  bf16* __restrict__ dx, float* __restrict__ partial,
+                  int d, long long rows_per_batch, long long ld_mod,
                   int rows_per_block, int blocks_per_batch) {
-  extern __shared__ float red[];  // [2][d]
+  extern __shared__ float red[];  // [BWD_WARPS][2][d]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long b = blockIdx.x / blocks_per_batch;
   const int chunk = blockIdx.x % blocks_per_batch;
@@ -105,8 +149,6 @@ ln_mod_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
   long long r1 = r0 + rows_per_block;
   if (r1 > (b + 1) * rows_per_batch) r1 = (b + 1) * rows_per_batch;
 
-  for (int i = threadIdx.x; i < 2 * d; i += ROW_THREADS) red[i] = 0.f;
-  __syncthreads();
 
   float one_plus[NC][8];
   {
@@ -132,7 +174,7 @@ ln_mod_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
 #pragma unroll
     for (int j = 0; j < 8; ++j) a_sh[c][j] = a_sc[c][j] = 0.f;
 
-  for (long long row = r0 + warp; row < r1; row += ROW_WARPS) {
+  for (long long row = r0 + warp; row < r1; row += BWD_WARPS) {
     float g[NC][8], xh[NC][8];
     load_row<NC>(dy + row * d, d, lane, g);
     load_row<NC>(x + row * d, d, lane, xh);
@@ -174,42 +216,25 @@ ln_mod_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
       }
     }
   }
-#pragma unroll
-  for (int c = 0; c < NC; ++c) {
-    const int col = c * 256 + lane * 8;
-    if (col < d) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        atomicAdd(&red[col + j], a_sh[c][j]);
-        atomicAdd(&red[d + col + j], a_sc[c][j]);
-      }
-    }
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < d; i += ROW_THREADS) {
-    atomicAdd(dshift + b * ld_dmod + i, red[i]);
-    atomicAdd(dscale + b * ld_dmod + i, red[d + i]);
-  }
+  block_fold_partials<NC>(red, a_sh, a_sc, partial + (long long)blockIdx.x * 2 * d, d, warp, lane);
 }
 
 // ------------------------------------------------------------------ gate bwd
 // forward was o = a*g[b] + x.  da = do*g[b]; dg[b] += sum_rows do*a;
 // dab[b] += sum_rows da (per-batch partial of the bias gradient, optional).
 template <int NC>
-__global__ void __launch_bounds__(ROW_THREADS)
+__global__ void __launch_bounds__(BWD_THREADS)
 gate_bwd_kernel(const bf16* __restrict__ dout, const bf16* __restrict__ a,
-                const bf16* __restrict__ gate, bf16* __restrict__ da, float* __restrict__ dgate,
-                float* __restrict__ dab, int d, long long rows_per_batch, long long ld_gate,
-                long long ld_dgate, long long ld_dab, int rows_per_block, int blocks_per_batch) {
-  extern __shared__ float red[];  // [2][d]
+                const bf16* __restrict__ gate, bf16* __restrict__ da, float* __restrict__ partial,
+                int d, long long rows_per_batch, long long ld_gate, int rows_per_block,
+                int blocks_per_batch) {
+  extern __shared__ float red[];  // [BWD_WARPS][2][d]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long b = blockIdx.x / blocks_per_batch;
   const int chunk = blockIdx.x % blocks_per_batch;
   const long long r0 = b * rows_per_batch + (long long)chunk * rows_per_block;
   long long r1 = r0 + rows_per_block;
   if (r1 > (b + 1) * rows_per_batch) r1 = (b + 1) * rows_per_batch;
-  for (int i = threadIdx.x; i < 2 * d; i += ROW_THREADS) red[i] = 0.f;
-  __syncthreads();
   float g[NC][8];
   load_row<NC>(gate + b * ld_gate, d, lane, g);
   float a_g[NC][8], a_b[NC][8];
@@ -217,7 +242,7 @@ gate_bwd_kernel(const bf16* __restrict__ dout, const bf16* __restrict__ a,
   for (int c = 0; c < NC; ++c)
 #pragma unroll
     for (int j = 0; j < 8; ++j) a_g[c][j] = a_b[c][j] = 0.f;
-  for (long long row = r0 + warp; row < r1; row += ROW_WARPS) {
+  for (long long row = r0 + warp; row < r1; row += BWD_WARPS) {
     float dv[NC][8], av[NC][8];
     load_row<NC>(dout + row * d, d, lane, dv);
     load_row<NC>(a + row * d, d, lane, av);
@@ -236,22 +261,7 @@ gate_bwd_kernel(const bf16* __restrict__ dout, const bf16* __restrict__ a,
       }
     }
   }
-#pragma unroll
-  for (int c = 0; c < NC; ++c) {
-    const int col = c * 256 + lane * 8;
-    if (col < d) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        atomicAdd(&red[col + j], a_g[c][j]);
-        atomicAdd(&red[d + col + j], a_b[c][j]);
-      }
-    }
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < d; i += ROW_THREADS) {
-    atomicAdd(dgate + b * ld_dgate + i, red[i]);
-    if (dab) atomicAdd(dab + b * ld_dab + i, red[d + i]);
-  }
+  block_fold_partials<NC>(red, a_g, a_b, partial + (long long)blockIdx.x * 2 * d, d, warp, lane);
 }
 
 // ------------------------------------------------------- text RMSNorm * scalar
@@ -391,38 +401,53 @@ int mmdit_ln_modulate_fwd(const void* x, const void* shift, const void* scale, v
   return check_launch("ln_mod_fwd_kernel");
 }
 
+int64_t mmdit_rowreduce_workspace_floats(int64_t rows, int32_t d, int64_t rows_per_batch) {
+  if (rows <= 0 || d <= 0 || rows_per_batch <= 0) return 0;
+  const int64_t bpb = (rows_per_batch + 31) / 32;
+  return (rows / rows_per_batch) * bpb * 2 * d;
+}
+
 int mmdit_ln_modulate_bwd(const void* dy, const void* x, const float* mean, const float* rstd,
                           const void* scale, const void* dres, void* dx, float* dshift,
-                          float* dscale, int64_t rows, int32_t d, int64_t rows_per_batch,
-                          int64_t ld_mod, int64_t ld_dmod, void* stream) {
-  MMDIT_REQUIRE(dy && x && mean && rstd && scale && dx && dshift && dscale && rows > 0 &&
+                          float* dscale, float* workspace, int64_t rows, int32_t d,
+                          int64_t rows_per_batch, int64_t ld_mod, int64_t ld_dmod, void* stream) {
+  MMDIT_REQUIRE(dy && x && mean && rstd && scale && dx && dshift && dscale && workspace && rows > 0 &&
                     d % 8 == 0 && rows_per_batch > 0 && rows % rows_per_batch == 0,
                 MMDIT_ERR_ARG, "ln_modulate_bwd: bad arguments");
-  const int rpb = 16;  // 2 rows per warp: >2 waves of blocks at cfg2 sizes, few atomics
+  const int rpb = 32;
   const int bpb = (int)((rows_per_batch + rpb - 1) / rpb);
-  const unsigned grid = (unsigned)((rows / rows_per_batch) * bpb);
-  const size_t smem = 2 * (size_t)d * sizeof(float);
-  DISPATCH_NC(d, (ln_mod_bwd_kernel<NC><<<grid, ROW_THREADS, smem, (cudaStream_t)stream>>>(
+  const int nb = (int)(rows / rows_per_batch);
+  const unsigned grid = (unsigned)(nb * bpb);
+  const size_t smem = (size_t)BWD_WARPS * 2 * d * sizeof(float);
+  MMDIT_REQUIRE(smem <= 48 * 1024, MMDIT_ERR_UNSUPPORTED, "ln_modulate_bwd: d=%d too wide", d);
+  DISPATCH_NC(d, (ln_mod_bwd_kernel<NC><<<grid, BWD_THREADS, smem, (cudaStream_t)stream>>>(
                      (const bf16*)dy, (const bf16*)x, mean, rstd, (const bf16*)scale,
-                     (const bf16*)dres, (bf16*)dx, dshift, dscale, d, rows_per_batch, ld_mod,
-                     ld_dmod, rpb, bpb)));
-  return check_launch("ln_mod_bwd_kernel");
+                     (const bf16*)dres, (bf16*)dx, workspace, d, rows_per_batch, ld_mod, rpb, bpb)));
+  dim3 g2((2 * d + 255) / 256, nb);
+  fold_batch_partials_kernel<<<g2, 256, 0, (cudaStream_t)stream>>>(workspace, dshift, dscale, d, bpb,
+                                                                  ld_dmod, ld_dmod);
+  return check_launch("ln_mod_bwd_kernel", 2);
 }
 
 int mmdit_gate_bwd(const void* dout, const void* a, const void* gate, void* da, float* dgate,
-                   float* dab, int64_t rows, int32_t d, int64_t rows_per_batch, int64_t ld_gate,
-                   int64_t ld_dgate, int64_t ld_dab, void* stream) {
-  MMDIT_REQUIRE(dout && a && gate && da && dgate && rows > 0 && d % 8 == 0 && rows_per_batch > 0 &&
-                    rows % rows_per_batch == 0,
+                   float* dab, float* workspace, int64_t rows, int32_t d, int64_t rows_per_batch,
+                   int64_t ld_gate, int64_t ld_dgate, int64_t ld_dab, void* stream) {
+  MMDIT_REQUIRE(dout && a && gate && da && dgate && workspace && rows > 0 && d % 8 == 0 &&
+                    rows_per_batch > 0 && rows % rows_per_batch == 0,
                 MMDIT_ERR_ARG, "gate_bwd: bad arguments");
-  const int rpb = 16;  // 2 rows per warp: >2 waves of blocks at cfg2 sizes, few atomics
+  const int rpb = 32;
   const int bpb = (int)((rows_per_batch + rpb - 1) / rpb);
-  const unsigned grid = (unsigned)((rows / rows_per_batch) * bpb);
-  const size_t smem = 2 * (size_t)d * sizeof(float);
-  DISPATCH_NC(d, (gate_bwd_kernel<NC><<<grid, ROW_THREADS, smem, (cudaStream_t)stream>>>(
-                     (const bf16*)dout, (const bf16*)a, (const bf16*)gate, (bf16*)da, dgate, dab, d,
-                     rows_per_batch, ld_gate, ld_dgate, ld_dab, rpb, bpb)));
-  return check_launch("gate_bwd_kernel");
+  const int nb = (int)(rows / rows_per_batch);
+  const unsigned grid = (unsigned)(nb * bpb);
+  const size_t smem = (size_t)BWD_WARPS * 2 * d * sizeof(float);
+  MMDIT_REQUIRE(smem <= 48 * 1024, MMDIT_ERR_UNSUPPORTED, "gate_bwd: d=%d too wide", d);
+  DISPATCH_NC(d, (gate_bwd_kernel<NC><<<grid, BWD_THREADS, smem, (cudaStream_t)stream>>>(
+                     (const bf16*)dout, (const bf16*)a, (const bf16*)gate, (bf16*)da, workspace, d,
+                     rows_per_batch, ld_gate, rpb, bpb)));
+  dim3 g2((2 * d + 255) / 256, nb);
+  fold_batch_partials_kernel<<<g2, 256, 0, (cudaStream_t)stream>>>(workspace, dgate, dab, d, bpb,
+                                                                  ld_dgate, ld_dab);
+  return check_launch("gate_bwd_kernel", 2);
 }
 
 int mmdit_text_norm_fwd(const void* c, const float* w1, const float* w2, const float* sigma1,

@@ -14,15 +14,15 @@ SIGNATURES = {
     "mmdit_attn_fwd": [vp, vp],
     "mmdit_attn_bwd": [vp, vp],
     "mmdit_ln_modulate_fwd": [vp, vp, vp, vp, vp, vp, i64, i32, i64, i64, f32, vp],
-    "mmdit_ln_modulate_bwd": [vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, i64, i64, i64, vp],
+    "mmdit_ln_modulate_bwd": [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, i64, i64, i64, vp],
     "mmdit_gate_residual_fwd": [vp, vp, vp, vp, i64, i32, i64, i64, vp],
-    "mmdit_gate_bwd": [vp, vp, vp, vp, vp, vp, i64, i32, i64, i64, i64, i64, vp],
+    "mmdit_gate_bwd": [vp, vp, vp, vp, vp, vp, vp, i64, i32, i64, i64, i64, i64, vp],
     "mmdit_text_norm_fwd": [vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, f32, vp],
     "mmdit_text_norm_bwd": [vp, vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, i32, vp],
     "mmdit_qknorm_rope_fwd": [vp, vp, vp, vp, vp, vp, i64, i32, i64, i64, i32, f32, vp],
     "mmdit_qknorm_rope_bwd": [vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, i64, i64, i64, i32, f32, vp],
     "mmdit_swiglu_fwd": [vp, vp, i64, i32, vp],
-    "mmdit_swiglu_bwd": [vp, vp, vp, vp, i64, i32, vp],
+    "mmdit_swiglu_bwd": [vp, vp, vp, vp, vp, i64, i32, vp],
     "mmdit_timestep_embed_fwd": [vp, vp, vp, vp, i32, i32, vp],
     "mmdit_timestep_embed_bwd": [vp, vp, vp, vp, vp, i32, i32, vp],
     "mmdit_patchify": [vp, i32, vp, i32, i32, i32, i32, i32, vp],
@@ -36,4 +36,12 @@ SIGNATURES = {
     "mmdit_cast_f32_bf16": [vp, vp, i64, vp],
     "mmdit_adamw_step": [vp, vp, i32, vp, f32, f32, f32, f32, f32, f32, vp],
     "mmdit_adamw_chunk_elems": [],
+    "mmdit_rowreduce_workspace_floats": [i64, i32, i64],
+    "mmdit_swiglu_bwd_workspace_floats": [i64, i32],
+}
+
+# entry points that do not return the int status code
+RESTYPES = {
+    "mmdit_rowreduce_workspace_floats": i64,
+    "mmdit_swiglu_bwd_workspace_floats": i64,
 }

@@ -80,7 +80,7 @@ def _declare(L):
     from . import _abi
     for name, argtypes in _abi.SIGNATURES.items():
         fn = getattr(L, name)
-        fn.restype = c_i32
+        fn.restype = _abi.RESTYPES.get(name, c_i32)
         fn.argtypes = argtypes
 
 

@@ -34,6 +34,11 @@ def _s():
     return torch.cuda.current_stream().cuda_stream
 
 
+def _workspace(nfloats, device):
+    """Scratch fp32 buffer from PyTorch's caching allocator (the library never allocates)."""
+    return torch.empty(int(nfloats), device=device, dtype=F32)
+
+
 def _rowmajor2d(t, name):
     if t.dim() != 2 or t.stride(1) != 1:
         raise ValueError(f"{name}: expected a 2-D tensor with unit inner stride, got {tuple(t.shape)} {t.stride()}")
@@ -170,8 +175,9 @@ def ln_modulate_bwd(dy, x, mean, rstd, scale, dres, dshift, dscale, rows_per_bat
     dx = torch.empty_like(x)
     assert dy.is_contiguous() and x.is_contiguous() and (dres is None or dres.is_contiguous())
     assert dshift.stride(0) == dscale.stride(0)
+    ws = _workspace(_lib.lib().mmdit_rowreduce_workspace_floats(R, d, rows_per_batch), x.device)
     _lib.check(_lib.lib().mmdit_ln_modulate_bwd(
-        _p(dy), _p(x), _p(mean), _p(rstd), _p(scale), _p(dres), _p(dx), _p(dshift), _p(dscale),
+        _p(dy), _p(x), _p(mean), _p(rstd), _p(scale), _p(dres), _p(dx), _p(dshift), _p(dscale), _p(ws),
         R, d, rows_per_batch, scale.stride(0), dshift.stride(0), _s()), "mmdit_ln_modulate_bwd")
     return dx
 
@@ -180,8 +186,9 @@ def gate_bwd(dout, a, gate, dgate, dab, rows_per_batch):
     R, d = dout.shape
     da = torch.empty_like(dout)
     assert dout.is_contiguous() and a.is_contiguous()
+    ws = _workspace(_lib.lib().mmdit_rowreduce_workspace_floats(R, d, rows_per_batch), dout.device)
     _lib.check(_lib.lib().mmdit_gate_bwd(
-        _p(dout), _p(a), _p(gate), _p(da), _p(dgate), _p(dab), R, d, rows_per_batch,
+        _p(dout), _p(a), _p(gate), _p(da), _p(dgate), _p(dab), _p(ws), R, d, rows_per_batch,
         gate.stride(0), dgate.stride(0), 0 if dab is None else dab.stride(0), _s()),
         "mmdit_gate_bwd")
     return da
@@ -242,7 +249,10 @@ def swiglu_bwd(da, h12, db12):
     R, two_h = h12.shape
     assert da.is_contiguous() and h12.is_contiguous()
     dh12 = torch.empty_like(h12)
-    _lib.check(_lib.lib().mmdit_swiglu_bwd(_p(da), _p(h12), _p(dh12), _p(db12), R, two_h // 2, _s()),
+    ws = None
+    if db12 is not None:
+        ws = _workspace(_lib.lib().mmdit_swiglu_bwd_workspace_floats(R, two_h // 2), h12.device)
+    _lib.check(_lib.lib().mmdit_swiglu_bwd(_p(da), _p(h12), _p(dh12), _p(db12), _p(ws), R, two_h // 2, _s()),
                "mmdit_swiglu_bwd")
     return dh12
 

@@ -16,7 +16,7 @@ HEADER = os.path.join(ROOT, "include", "mmdit_b200.h")
 def _declared():
     src = open(HEADER).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return re.findall(r"\b(?:int|const char\*|unsigned long long)\s+(mmdit_\w+)\s*\(", src)
+    return re.findall(r"\b(?:int|int64_t|const char\*|unsigned long long)\s+(mmdit_\w+)\s*\(", src)
 
 
 def test_library_exports_every_declared_symbol():

@@ -197,7 +197,7 @@ def run_product(args):
     if world > 1:  # DDP ctor semantics: every replica starts from rank 0's weights
         for p in model.parameters():
             dist.broadcast(p.data, 0)
-    trainer = RFTrainer(model, world_size=world, use_graph=(world == 1 and not args.no_graph))
+    trainer = RFTrainer(model, world_size=world, use_graph=not args.no_graph)
     C = CFG2["inCh"]
     nb = 4  # distinct host batches (3.3 MB each of text would be L2-resident; activations are not:
     #         one step touches > 20 GB of HBM, far beyond the 126 MB L2, so no explicit flush is needed)
@@ -253,13 +253,15 @@ def run_product(args):
 
     # ---- per-kernel-class roofline from an instrumented, untimed step (eager, same shapes).
     # Runs on EVERY rank: with data parallelism the backward launches gradient all-reduces.
-    probe = RFTrainer(model, world_size=1, use_graph=False) if trainer.use_graph else trainer
-    probe._zero(); probe._fwd_bwd(fresh(1)); probe._update()     # eager warm-up of the probe path
+    # (uses the trainer's eager building blocks; no optimizer step, nothing is replayed afterwards)
+    def close_reduce():
+        if trainer.buckets is not None:
+            trainer.buckets.finish()
+    trainer._zero(); trainer._fwd_bwd(fresh(1)); close_reduce()   # eager warm-up of the probe path
     c1 = _lib.launch_count()
-    kern = instrument_kernels(probe, fresh(0))
-    launches_per_step = _lib.launch_count() - c1
-    if world > 1:
-        probe._update()
+    kern = instrument_kernels(trainer, fresh(0))
+    launches_per_step = _lib.launch_count() - c1 + 3              # + the 3 optimizer kernels of a real step
+    close_reduce()
     barrier()
 
     if rank != 0:

@@ -86,6 +86,7 @@ class GradBuckets:
 
     # ---- overlap: launch a bucket's all-reduce the moment its last gradient has landed
     def install_hooks(self):
+        self.overlap = True
         self._count = [0] * len(self.buckets)
         self._works = [None] * len(self.buckets)
         for bi, (_, _, ps) in enumerate(self.buckets):
@@ -102,8 +103,18 @@ class GradBuckets:
 
     def _ready(self, bi):
         self._count[bi] += 1
-        if self.world_size > 1 and self._count[bi] == len(self.buckets[bi][2]):
+        if self.overlap and self.world_size > 1 and self._count[bi] == len(self.buckets[bi][2]):
             self._launch(bi)
+
+    def all_reduce_mean(self):
+        """Non-overlapped variant: reduce every bucket now (async launches, then wait + mean)."""
+        if self.world_size == 1:
+            return
+        works = [dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+                 for _, flat, _ in self.buckets]
+        for w, (_, flat, _) in zip(works, self.buckets):
+            w.wait()
+            flat.mul_(1.0 / self.world_size)
 
     def finish(self):
         """Wait for every bucket (launching the ones no hook fired for) and apply DDP's mean."""
@@ -124,7 +135,7 @@ class RFTrainer:
         self.device = next(model.parameters()).device
         self.clip = clip
         self.world_size = world_size
-        self.use_graph = use_graph and world_size == 1
+        self.use_graph = use_graph
         self.params = [p for p in model.parameters() if p.requires_grad]
         self.buckets = GradBuckets(list(model.named_parameters()), world_size, process_group,
                                    self.device) if world_size > 1 else None
@@ -139,6 +150,7 @@ class RFTrainer:
                                          fused=True, capturable=self.use_graph)
         self._bound = False
         self.graph = None
+        self.graph_opt = None
         self.static = None
         self.loss = None
         self.kernel_launches = None
@@ -192,6 +204,11 @@ class RFTrainer:
         for k, v in batch.items():
             self.static[k].copy_(v, non_blocking=True)
         self.graph.replay()
+        if self.graph_opt is not None:
+            # data parallel: the all-reduce sits between the two captured halves of the step
+            # (capturing NCCL work issued from autograd hooks hung in testing on this stack)
+            self.buckets.all_reduce_mean()
+            self.graph_opt.replay()
         return self.loss
 
     def _capture(self, batch):
@@ -201,12 +218,24 @@ class RFTrainer:
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
             for _ in range(3):
-                self.opt.zero_grad(set_to_none=True)
+                self._zero()
                 self._fwd_bwd(self.static)
                 self._update()
         torch.cuda.current_stream().wait_stream(s)
-        self.opt.zero_grad(set_to_none=True)
+        torch.cuda.synchronize()
+        self._zero()
         self.graph = torch.cuda.CUDAGraph()
+        self.graph_opt = None
+        if self.buckets is None:
+            with torch.cuda.graph(self.graph):
+                self.loss = self._fwd_bwd(self.static)
+                self._update()
+            return
+        self.buckets.overlap = False            # hooks stay silent while capturing / replaying
         with torch.cuda.graph(self.graph):
+            self.buckets.zero()                  # buckets persist across replays: clear inside the graph
             self.loss = self._fwd_bwd(self.static)
-            self._update()
+        self.buckets.all_reduce_mean()
+        self.graph_opt = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph_opt):
+            self.opt.step() if self.fused_optimizer else self._update()

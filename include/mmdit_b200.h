@@ -65,7 +65,8 @@ typedef struct mmdit_gemm_args {
   int32_t a_major, b_major;
   int32_t d_fp32;     /* 0: bf16 output, 1: fp32 output */
   int32_t accumulate; /* fp32 output only: D += result (atomic when split_k > 1) */
-  int32_t split_k;    /* 0 = auto (only >1 when accumulate=1) */
+  int32_t split_k;    /* 0 = auto (only >1 when accumulate=1); >1 with accumulate=0: slices mode,
+                         split s writes D + s*M*ldd and the caller folds (mmdit_fold_slices_f32) */
   int32_t epilogue;   /* MMDIT_EPI_* */
   const void* bias;   /* [N] or NULL */
   int32_t bias_fp32;  /* dtype of bias */
@@ -122,13 +123,13 @@ int mmdit_attn_bwd(const mmdit_attn_args* args, void* stream);
  * y = LN(x) * (1 + scale[b]) + shift[b], LN eps, no affine (Norm.py:16-23).
  * shift/scale: bf16 [B, d] with row stride ld_mod; b = row / rows_per_batch.
  * bwd: dx = LN-backward(dy * (1+scale)) (+ dres), dshift/dscale (fp32, row
- * stride ld_dmod) are WRITTEN (two-stage reduction through `workspace`). */
+ * stride ld_dmod; bf16 when dmod_bf16) are WRITTEN (two-stage reduction through `workspace`). */
 int mmdit_ln_modulate_fwd(const void* x, const void* shift, const void* scale, void* y, float* mean,
                           float* rstd, int64_t rows, int32_t d, int64_t rows_per_batch,
                           int64_t ld_mod, float eps, void* stream);
 int mmdit_ln_modulate_bwd(const void* dy, const void* x, const float* mean, const float* rstd,
-                          const void* scale, const void* dres, void* dx, float* dshift,
-                          float* dscale, float* workspace, int64_t rows, int32_t d,
+                          const void* scale, const void* dres, void* dx, void* dshift,
+                          void* dscale, int32_t dmod_bf16, float* workspace, int64_t rows, int32_t d,
                           int64_t rows_per_batch, int64_t ld_mod, int64_t ld_dmod, void* stream);
 /* fp32 elements of `workspace` needed by ln_modulate_bwd / gate_bwd (per-block partial sums;
  * the column reductions are two-stage, no atomics). */
@@ -142,9 +143,10 @@ int64_t mmdit_rowreduce_workspace_floats(int64_t rows, int32_t d, int64_t rows_p
 int mmdit_gate_residual_fwd(const void* a, const void* gate, const void* resid, void* out,
                             int64_t rows, int32_t d, int64_t rows_per_batch, int64_t ld_gate,
                             void* stream);
-int mmdit_gate_bwd(const void* dout, const void* a, const void* gate, void* da, float* dgate,
-                   float* dab, float* workspace, int64_t rows, int32_t d, int64_t rows_per_batch,
-                   int64_t ld_gate, int64_t ld_dgate, int64_t ld_dab, void* stream);
+int mmdit_gate_bwd(const void* dout, const void* a, const void* gate, void* da, void* dgate,
+                   int32_t dgate_bf16, float* dab, float* workspace, int64_t rows, int32_t d,
+                   int64_t rows_per_batch, int64_t ld_gate, int64_t ld_dgate, int64_t ld_dab,
+                   void* stream);
 
 /* Text front-end (diff_model.py:168-172,323-326): out = bf16(sigma * RMSNorm_fp32(c) * w).
  * Tokens [0,split) of each sample use (w1,sigma1) -> out1 [B*split, d]; tokens [split,M)
@@ -208,6 +210,10 @@ int mmdit_colsum_bf16(const void* in, float* out, int64_t rows, int32_t n, int64
 int mmdit_fold_rows_f32(const float* in, float* out, int32_t rows, int32_t n, int64_t ld,
                         void* stream);
 int mmdit_cast_f32_bf16(const float* in, void* out, int64_t n, void* stream);
+/* out[i] (+)= sum_s ws[s*stride + i]: folds the slices of a split-K GEMM launched with
+ * split_k > 1, accumulate = 0 (each split then writes its partial product to D + s*M*ldd). */
+int mmdit_fold_slices_f32(const float* ws, float* out, int64_t n, int32_t slices, int64_t stride,
+                          int32_t accumulate, void* stream);
 
 /* ---------------------------------------------------------- optimizer step --
  * Fused gradient-norm clip + AdamW + bf16 shadow refresh over many tensors

@@ -444,6 +444,22 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ in, bf16* __restr
     out[i] = __float2bfloat16(in[i]);
 }
 
+// out[i] (+)= sum_s ws[s*stride + i]   -- folds split-K slices (fp32, 16-byte vectors)
+__global__ void __launch_bounds__(256)
+fold_slices_kernel(const float* __restrict__ ws, float* __restrict__ out, long long n, int slices,
+                   long long stride, int accumulate) {
+  const long long n4 = n / 4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4;
+       i += (long long)gridDim.x * blockDim.x) {
+    float4 acc = accumulate ? reinterpret_cast<const float4*>(out)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int s = 0; s < slices; ++s) {
+      const float4 v = reinterpret_cast<const float4*>(ws + s * stride)[i];
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    reinterpret_cast<float4*>(out)[i] = acc;
+  }
+}
+
 static inline unsigned grid_for(long long work_items, int threads) {
   long long blocks = (work_items + threads - 1) / threads;
   const long long cap = (long long)num_sms() * 16;
@@ -659,6 +675,16 @@ int mmdit_fold_rows_f32(const float* in, float* out, int32_t rows, int32_t n, in
   MMDIT_REQUIRE(in && out && rows > 0 && n > 0, MMDIT_ERR_ARG, "fold_rows_f32: bad arguments");
   fold_rows_f32_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(in, out, rows, n, ld);
   return check_launch("fold_rows_f32_kernel");
+}
+
+int mmdit_fold_slices_f32(const float* ws, float* out, int64_t n, int32_t slices, int64_t stride,
+                          int32_t accumulate, void* stream) {
+  MMDIT_REQUIRE(ws && out && n > 0 && n % 4 == 0 && slices > 0 && stride % 4 == 0 &&
+                    ((uintptr_t)ws & 15) == 0 && ((uintptr_t)out & 15) == 0,
+                MMDIT_ERR_ARG, "fold_slices_f32: bad arguments");
+  fold_slices_kernel<<<grid_for(n / 4, 256), 256, 0, (cudaStream_t)stream>>>(ws, out, n, slices, stride,
+                                                                             accumulate);
+  return check_launch("fold_slices_kernel");
 }
 
 int mmdit_cast_f32_bf16(const float* in, void* out, int64_t n, void* stream) {

@@ -49,6 +49,7 @@ struct GemmParams {
   bf16* aux;
   long long ld_aux;
   long long remap_rows, remap_batch_rows, remap_offset;
+  long long slice_stride;  // split-K slices mode: split ks writes D + ks*slice_stride (no atomics)
   int debug;  // bit0: skip global stores, bit1: skip TMEM loads (perf experiments only)
 };
 
@@ -166,7 +167,8 @@ __device__ __forceinline__ void gate_prefetch(const GemmParams& p, int lane, lon
 
 template <int EV>
 __device__ __forceinline__ void epilogue_fast(const GemmParams& p, const float* wbuf, int lane,
-                                              long long m0, int n, const GatePrefetch* pf) {
+                                              long long m0, int n, const GatePrefetch* pf,
+                                              long long slice_off) {
   const int sub_row = lane >> 3, seg = lane & 7;
   float bias[8];
   if constexpr (EV == EV_BF16_BIAS || EV == EV_GATE) {
@@ -208,7 +210,7 @@ __device__ __forceinline__ void epilogue_fast(const GemmParams& p, const float* 
     if constexpr (EV == EV_BF16 || EV == EV_BF16_BIAS || EV == EV_GATE) {
       store8(reinterpret_cast<bf16*>(p.D) + m * p.ldd + n, v);
     } else if constexpr (EV == EV_F32) {
-      float* dp = reinterpret_cast<float*>(p.D) + m * p.ldd + n;
+      float* dp = reinterpret_cast<float*>(p.D) + slice_off + m * p.ldd + n;
       *reinterpret_cast<float4*>(dp) = make_float4(v[0], v[1], v[2], v[3]);
       *reinterpret_cast<float4*>(dp + 4) = make_float4(v[4], v[5], v[6], v[7]);
     } else if constexpr (EV == EV_F32_ATOMIC) {
@@ -389,7 +391,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
         const int n = n_blk * block_n + c * 64 + seg * 8;
         if constexpr (EV != EV_GENERIC) {
           if (n < p.N && !(p.debug & 1))
-            epilogue_fast<EV>(p, wbuf, lane, m0, n, &pf);
+            epilogue_fast<EV>(p, wbuf, lane, m0, n, &pf, (work % p.split_k) * p.slice_stride);
         } else {
           const int nvalid = min(8, p.N - n);
 #pragma unroll 1
@@ -501,8 +503,12 @@ extern "C" int mmdit_gemm_bf16(const mmdit_gemm_args* a, void* stream_) {
       }
     }
   }
-  MMDIT_REQUIRE(split == 1 || (a->accumulate && a->d_fp32), MMDIT_ERR_ARG,
-                "gemm: split_k > 1 needs fp32 accumulate output");
+  // split_k > 1 with accumulate=0: "slices" mode -- split s writes its partial product to
+  // D + s*M*ldd (D must hold split_k such slices); the caller folds them (no atomics).
+  MMDIT_REQUIRE(split == 1 || a->d_fp32, MMDIT_ERR_ARG, "gemm: split_k > 1 needs fp32 output");
+  const bool slices = split > 1 && !a->accumulate;
+  MMDIT_REQUIRE(!slices || (a->epilogue == MMDIT_EPI_NONE && !a->bias && !a->aux && a->remap_rows == 0),
+                MMDIT_ERR_ARG, "gemm: split-K slices mode supports the plain fp32 epilogue only");
   if (split > p.kb_total) split = p.kb_total;
   p.kb_per_split = (p.kb_total + split - 1) / split;
   p.split_k = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
@@ -517,6 +523,7 @@ extern "C" int mmdit_gemm_bf16(const mmdit_gemm_args* a, void* stream_) {
   p.remap_rows = a->remap_rows; p.remap_batch_rows = a->remap_batch_rows;
   p.remap_offset = a->remap_offset;
   p.debug = a->reserved;
+  p.slice_stride = (split > 1 && !a->accumulate) ? (long long)a->M * a->ldd : 0;
 
   // Tensor maps. dims are innermost-first.
   {
@@ -573,6 +580,8 @@ extern "C" int mmdit_gemm_bf16(const mmdit_gemm_args* a, void* stream_) {
     }                                                                                             \
     gemm_tcgen05_kernel<EVV><<<grid, GEMM_THREADS, smem_bytes, stream>>>(p);                      \
   } break;
+  MMDIT_REQUIRE(p.slice_stride == 0 || ev == EV_F32, MMDIT_ERR_ALIGN,
+                "gemm: split-K slices mode needs N %% 8 == 0 and 16-byte aligned D");
   switch (ev) {
     LAUNCH_EV(EV_GENERIC)
     LAUNCH_EV(EV_BF16)

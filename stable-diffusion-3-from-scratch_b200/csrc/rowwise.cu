@@ -47,17 +47,23 @@ __device__ __forceinline__ void block_fold_partials(float* red, const float (&a0
 }
 
 // out0[b, col] = sum_k partial[b, k, 0, col]; out1[b, col] = sum_k partial[b, k, 1, col]
-__global__ void fold_batch_partials_kernel(const float* __restrict__ partial, float* __restrict__ out0,
-                                           float* __restrict__ out1, int d, int blocks_per_batch,
-                                           long long ld0, long long ld1) {
+// Outputs are fp32, or bf16 when out_bf16 is set (gradients of the bf16 modulation vectors).
+__global__ void fold_batch_partials_kernel(const float* __restrict__ partial, void* __restrict__ out0,
+                                           void* __restrict__ out1, int d, int blocks_per_batch,
+                                           long long ld0, long long ld1, int out0_bf16, int out1_bf16) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;  // 0 .. 2d
   if (i >= 2 * d) return;
   const long long b = blockIdx.y;
   const float* src = partial + b * blocks_per_batch * 2 * d + i;
   float acc = 0.f;
   for (int k = 0; k < blocks_per_batch; ++k) acc += src[(long long)k * 2 * d];
-  if (i < d) out0[b * ld0 + i] = acc;
-  else if (out1) out1[b * ld1 + (i - d)] = acc;
+  if (i < d) {
+    if (out0_bf16) reinterpret_cast<bf16*>(out0)[b * ld0 + i] = __float2bfloat16(acc);
+    else reinterpret_cast<float*>(out0)[b * ld0 + i] = acc;
+  } else if (out1) {
+    if (out1_bf16) reinterpret_cast<bf16*>(out1)[b * ld1 + (i - d)] = __float2bfloat16(acc);
+    else reinterpret_cast<float*>(out1)[b * ld1 + (i - d)] = acc;
+  }
 }
 
 template <int NC>
@@ -408,8 +414,8 @@ int64_t mmdit_rowreduce_workspace_floats(int64_t rows, int32_t d, int64_t rows_p
 }
 
 int mmdit_ln_modulate_bwd(const void* dy, const void* x, const float* mean, const float* rstd,
-                          const void* scale, const void* dres, void* dx, float* dshift,
-                          float* dscale, float* workspace, int64_t rows, int32_t d,
+                          const void* scale, const void* dres, void* dx, void* dshift,
+                          void* dscale, int32_t dmod_bf16, float* workspace, int64_t rows, int32_t d,
                           int64_t rows_per_batch, int64_t ld_mod, int64_t ld_dmod, void* stream) {
   MMDIT_REQUIRE(dy && x && mean && rstd && scale && dx && dshift && dscale && workspace && rows > 0 &&
                     d % 8 == 0 && rows_per_batch > 0 && rows % rows_per_batch == 0,
@@ -425,13 +431,14 @@ int mmdit_ln_modulate_bwd(const void* dy, const void* x, const float* mean, cons
                      (const bf16*)dres, (bf16*)dx, workspace, d, rows_per_batch, ld_mod, rpb, bpb)));
   dim3 g2((2 * d + 255) / 256, nb);
   fold_batch_partials_kernel<<<g2, 256, 0, (cudaStream_t)stream>>>(workspace, dshift, dscale, d, bpb,
-                                                                  ld_dmod, ld_dmod);
+                                                                  ld_dmod, ld_dmod, dmod_bf16, dmod_bf16);
   return check_launch("ln_mod_bwd_kernel", 2);
 }
 
-int mmdit_gate_bwd(const void* dout, const void* a, const void* gate, void* da, float* dgate,
-                   float* dab, float* workspace, int64_t rows, int32_t d, int64_t rows_per_batch,
-                   int64_t ld_gate, int64_t ld_dgate, int64_t ld_dab, void* stream) {
+int mmdit_gate_bwd(const void* dout, const void* a, const void* gate, void* da, void* dgate,
+                   int32_t dgate_bf16, float* dab, float* workspace, int64_t rows, int32_t d,
+                   int64_t rows_per_batch, int64_t ld_gate, int64_t ld_dgate, int64_t ld_dab,
+                   void* stream) {
   MMDIT_REQUIRE(dout && a && gate && da && dgate && workspace && rows > 0 && d % 8 == 0 &&
                     rows_per_batch > 0 && rows % rows_per_batch == 0,
                 MMDIT_ERR_ARG, "gate_bwd: bad arguments");
@@ -446,7 +453,7 @@ int mmdit_gate_bwd(const void* dout, const void* a, const void* gate, void* da, 
                      rows_per_batch, ld_gate, rpb, bpb)));
   dim3 g2((2 * d + 255) / 256, nb);
   fold_batch_partials_kernel<<<g2, 256, 0, (cudaStream_t)stream>>>(workspace, dgate, dab, d, bpb,
-                                                                  ld_dgate, ld_dab);
+                                                                  ld_dgate, ld_dab, dgate_bf16, 0);
   return check_launch("gate_bwd_kernel", 2);
 }
 

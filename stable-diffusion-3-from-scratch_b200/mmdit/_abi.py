@@ -14,9 +14,9 @@ SIGNATURES = {
     "mmdit_attn_fwd": [vp, vp],
     "mmdit_attn_bwd": [vp, vp],
     "mmdit_ln_modulate_fwd": [vp, vp, vp, vp, vp, vp, i64, i32, i64, i64, f32, vp],
-    "mmdit_ln_modulate_bwd": [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, i64, i64, i64, vp],
+    "mmdit_ln_modulate_bwd": [vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp, i64, i32, i64, i64, i64, vp],
     "mmdit_gate_residual_fwd": [vp, vp, vp, vp, i64, i32, i64, i64, vp],
-    "mmdit_gate_bwd": [vp, vp, vp, vp, vp, vp, vp, i64, i32, i64, i64, i64, i64, vp],
+    "mmdit_gate_bwd": [vp, vp, vp, vp, vp, i32, vp, vp, i64, i32, i64, i64, i64, i64, vp],
     "mmdit_text_norm_fwd": [vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, f32, vp],
     "mmdit_text_norm_bwd": [vp, vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, i32, vp],
     "mmdit_qknorm_rope_fwd": [vp, vp, vp, vp, vp, vp, i64, i32, i64, i64, i32, f32, vp],
@@ -34,6 +34,7 @@ SIGNATURES = {
     "mmdit_colsum_bf16": [vp, vp, i64, i32, i64, vp],
     "mmdit_fold_rows_f32": [vp, vp, i32, i32, i64, vp],
     "mmdit_cast_f32_bf16": [vp, vp, i64, vp],
+    "mmdit_fold_slices_f32": [vp, vp, i64, i32, i64, i32, vp],
     "mmdit_adamw_step": [vp, vp, i32, vp, f32, f32, f32, f32, f32, f32, vp],
     "mmdit_adamw_chunk_elems": [],
     "mmdit_rowreduce_workspace_floats": [i64, i32, i64],

@@ -96,12 +96,13 @@ class GatedLinearFn(Function):
         rpb = ctx.rpb
         do = do.contiguous()
         Bn, n = gate.shape
-        part = torch.zeros((2, Bn, n), device=do.device, dtype=F32)
-        da = ops.gate_bwd(do, aux, gate, part[0], part[1] if ctx.has_bias else None, rpb)
+        dgate = torch.empty((Bn, n), device=do.device, dtype=BF16)       # written by the kernel
+        dab = torch.empty((Bn, n), device=do.device, dtype=F32) if ctx.has_bias else None
+        da = ops.gate_bwd(do, aux, gate, dgate, dab, rpb)
         dx = ops.gemm(da, wb, b_major=1)
         dw = ops.gemm(da, a, a_major=1, b_major=1, out_dtype=F32)
-        db = part[1].sum(0) if ctx.has_bias else None
-        return dx, None, None, part[0].to(BF16), do, None, dw, db
+        db = dab.sum(0) if ctx.has_bias else None
+        return dx, None, None, dgate, do, None, dw, db
 
 
 class LNModulateFn(Function):
@@ -120,10 +121,9 @@ class LNModulateFn(Function):
     def backward(ctx, dy):
         x2, mean, rstd, scale = ctx.saved_tensors
         Bn, T, d = ctx.shape
-        dmod = torch.zeros((2, Bn, d), device=dy.device, dtype=F32)
+        dmod = torch.empty((2, Bn, d), device=dy.device, dtype=BF16)     # written by the kernel
         dx = ops.ln_modulate_bwd(dy.reshape(Bn * T, d).contiguous(), x2, mean, rstd, scale, None,
                                  dmod[0], dmod[1], T)
-        dmod = dmod.to(BF16)
         return dx.view(Bn, T, d), dmod[0], dmod[1]
 
 

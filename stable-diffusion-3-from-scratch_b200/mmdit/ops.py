@@ -39,6 +39,22 @@ def _workspace(nfloats, device):
     return torch.empty(int(nfloats), device=device, dtype=F32)
 
 
+def _plan_split(M, N, K, sms=148):
+    """Split-K factor for an fp32-output GEMM: minimise waves * (k-blocks per unit + epilogue)."""
+    tiles = ((M + 127) // 128) * ((N + 255) // 256)
+    kb = (K + 63) // 64
+    if tiles >= sms or kb < 16:
+        return 1
+    best, best_s = None, 1
+    for s in range(1, min(kb // 4, 32) + 1):
+        per = -(-kb // s)
+        units = tiles * (-(-kb // per))
+        t = -(-units // sms) * (per + 6.0) + (0.0 if s == 1 else 2.0 + 0.5 * s)
+        if best is None or t < best - 1e-9:
+            best, best_s = t, s
+    return best_s
+
+
 def _rowmajor2d(t, name):
     if t.dim() != 2 or t.stride(1) != 1:
         raise ValueError(f"{name}: expected a 2-D tensor with unit inner stride, got {tuple(t.shape)} {t.stride()}")
@@ -47,7 +63,7 @@ def _rowmajor2d(t, name):
 # --------------------------------------------------------------------- GEMM
 def gemm(A, B, *, a_major=0, b_major=0, out=None, out_dtype=BF16, accumulate=False, split_k=0,
          epilogue=EPI_NONE, bias=None, gate=None, rows_per_gate=0, resid=None, aux=None,
-         remap=None, out_rows=None, force_block_n=0, simt=False):
+         remap=None, out_rows=None, force_block_n=0, simt=False, _logical_m=None):
     """D[M,N] = epilogue(A @ B^T).  A is stored [M,K] (a_major=0) or [K,M] (a_major=1);
     B is stored [N,K] (b_major=0) or [K,N] (b_major=1)."""
     _need_cuda(A, B)
@@ -65,11 +81,19 @@ def gemm(A, B, *, a_major=0, b_major=0, out=None, out_dtype=BF16, accumulate=Fal
         # into an fp32 buffer, then one cast
         acc = gemm(A, B, a_major=a_major, b_major=b_major, out_dtype=F32, accumulate=True)
         return acc.to(BF16)
-    if out is None and out_dtype == F32 and not accumulate and remap is None and epilogue == EPI_NONE:
-        # wgrad-style outputs: few tiles, long reduction -> zero-init and let split-K atomics fill all SMs
-        if ((M + 127) // 128) * ((N + 255) // 256) < 120 and K >= 1024:
-            out = torch.zeros((M, N), device=A.device, dtype=F32)
-            accumulate = True
+    if (out is None and out_dtype == F32 and not accumulate and remap is None and epilogue == EPI_NONE
+            and bias is None and aux is None and not simt and N % 8 == 0 and split_k == 0):
+        # wgrad-style outputs (few tiles, long reduction): split-K so that every SM has work; each
+        # split writes its own fp32 slice (plain coalesced stores) and one small kernel folds them
+        s = _plan_split(M, N, K)
+        if s > 1:
+            ws = torch.empty((s, M, N), device=A.device, dtype=F32)
+            gemm(A, B, a_major=a_major, b_major=b_major, out=ws.view(s * M, N), split_k=s,
+                 force_block_n=force_block_n, _logical_m=M)
+            out = torch.empty((M, N), device=A.device, dtype=F32)
+            _lib.check(_lib.lib().mmdit_fold_slices_f32(_p(ws), _p(out), M * N, s, M * N, 0, _s()),
+                       "mmdit_fold_slices_f32")
+            return out
     if out is None:
         rows = out_rows if out_rows is not None else M
         if remap is not None and out_rows is None:
@@ -177,8 +201,8 @@ def ln_modulate_bwd(dy, x, mean, rstd, scale, dres, dshift, dscale, rows_per_bat
     assert dshift.stride(0) == dscale.stride(0)
     ws = _workspace(_lib.lib().mmdit_rowreduce_workspace_floats(R, d, rows_per_batch), x.device)
     _lib.check(_lib.lib().mmdit_ln_modulate_bwd(
-        _p(dy), _p(x), _p(mean), _p(rstd), _p(scale), _p(dres), _p(dx), _p(dshift), _p(dscale), _p(ws),
-        R, d, rows_per_batch, scale.stride(0), dshift.stride(0), _s()), "mmdit_ln_modulate_bwd")
+        _p(dy), _p(x), _p(mean), _p(rstd), _p(scale), _p(dres), _p(dx), _p(dshift), _p(dscale),
+        int(dshift.dtype == BF16), _p(ws), R, d, rows_per_batch, scale.stride(0), dshift.stride(0), _s()), "mmdit_ln_modulate_bwd")
     return dx
 
 
@@ -188,7 +212,8 @@ def gate_bwd(dout, a, gate, dgate, dab, rows_per_batch):
     assert dout.is_contiguous() and a.is_contiguous()
     ws = _workspace(_lib.lib().mmdit_rowreduce_workspace_floats(R, d, rows_per_batch), dout.device)
     _lib.check(_lib.lib().mmdit_gate_bwd(
-        _p(dout), _p(a), _p(gate), _p(da), _p(dgate), _p(dab), _p(ws), R, d, rows_per_batch,
+        _p(dout), _p(a), _p(gate), _p(da), _p(dgate), int(dgate.dtype == BF16), _p(dab), _p(ws), R, d,
+        rows_per_batch,
         gate.stride(0), dgate.stride(0), 0 if dab is None else dab.stride(0), _s()),
         "mmdit_gate_bwd")
     return da

@@ -155,9 +155,9 @@ int mmdit_text_norm_fwd(const void* c, const float* w1, const float* w2, const f
                         const float* sigma2, void* out1, void* out2, float* rstd, int64_t batch,
                         int32_t tokens, int32_t split, int32_t d, float eps, void* stream);
 /* One half: dn = grad wrt out half [B*ntok, d]; accumulates dw [d] and dsigma [1]. */
-int mmdit_text_norm_bwd(const void* dn, const void* c, const float* rstd, const float* w,
-                        const float* sigma, float* dw, float* dsigma, int64_t batch, int32_t tokens,
-                        int32_t tok0, int32_t ntok, int32_t d, void* stream);
+int mmdit_text_norm_bwd(const void* dn, int32_t dn_fp32, const void* c, const float* rstd,
+                        const float* w, const float* sigma, float* dw, float* dsigma, int64_t batch,
+                        int32_t tokens, int32_t tok0, int32_t ntok, int32_t d, void* stream);
 
 /* Per-head QK RMSNorm (+ 2-D axial RoPE on image tokens) (Attention.py:61-64,130-134,
  * 174-194; rotary_embedding.py:36-76,269-288).  qkv: raw projections, q at column 0 and

@@ -31,6 +31,17 @@ CONFIGS = {
                               attn_type="softmax", MLP_type="swiglu", num_blocks=3, device="cpu",
                               positional_encoding="RoPE2d"), B=3, h=24, w=40, M=154),
 }
+# lighter fixtures (loss, output, per-gradient bf16 floors only) for two more BASELINE shapes
+LIGHT = {
+    # width of BASELINE configs[2]/[3] (dim 1536, 24 heads) at depth 2
+    "wide": dict(model=dict(inCh=16, class_dim=768, patch_size=2, dim=1536, hidden_scale=4.0, num_heads=24,
+                            attn_type="softmax", MLP_type="swiglu", num_blocks=2, device="cpu",
+                            positional_encoding="RoPE2d"), B=2, h=32, w=32, M=154),
+    # 512 px: 64x64 latent -> 1024 image tokens, 256 text tokens (BASELINE configs[3] wording)
+    "px512": dict(model=dict(inCh=16, class_dim=768, patch_size=2, dim=256, hidden_scale=4.0, num_heads=4,
+                             attn_type="softmax", MLP_type="swiglu", num_blocks=2, device="cpu",
+                             positional_encoding="RoPE2d"), B=1, h=64, w=64, M=256),
+}
 FULL_GRADS = ["time_scale", "learnable_scalar", "learnable_scalar2", "out_proj.bias",
               "blocks.0.attn.q_norm_x.weight", "blocks.0.attn.k_norm_c.weight", "blocks.1.y_proj.0.bias",
               "blocks.0.MLP_x.MLP.w3.bias"]
@@ -55,6 +66,22 @@ def main():
     torch.set_num_threads(8)
     diff_model = import_reference()
     os.makedirs(os.path.join(ROOT, "tests", "golden"), exist_ok=True)
+    for name, cfg in LIGHT.items():
+        model = diff_model(**dict(cfg["model"], checkpoint_MLP=False, checkpoint_attn=False))
+        shapes = {k: tuple(v.shape) for k, v in model.state_dict().items()}
+        model.load_state_dict(O.synth_state_dict(shapes), strict=True)
+        batch = O.synth_batch(cfg["B"], cfg["model"]["inCh"], cfg["h"], cfg["w"], cfg["M"], seed=1000)
+        v32, l32, g32 = ref_step(model, batch, False)
+        v16, l16, g16 = ref_step(model, batch, True)
+        out = dict(config=cfg, loss_fp32=l32, loss_bf16=l16,
+                   v_absmax=float(v32.abs().max()), v_relerr_bf16=float((v16 - v32).abs().max() / v32.abs().max()),
+                   gradnorm_fp32={k: float(g.norm()) for k, g in g32.items()},
+                   grad_l2err_bf16={k: float((g16[k].float() - g).norm() / (g.norm() + 1e-30)) for k, g in g32.items()})
+        path = os.path.join(ROOT, "tests", "golden", f"{name}.pt")
+        torch.save(out, path)
+        worst = max(out["grad_l2err_bf16"].items(), key=lambda kv: kv[1])
+        print(name, "loss fp32", l32, "bf16", l16, "worst bf16 grad L2 err", worst, "->", path,
+              os.path.getsize(path) // 1024, "KiB")
     for name, cfg in CONFIGS.items():
         mk = dict(cfg["model"], checkpoint_MLP=False, checkpoint_attn=False)
         model = diff_model(**mk)

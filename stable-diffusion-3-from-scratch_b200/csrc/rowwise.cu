@@ -315,8 +315,25 @@ text_norm_fwd_kernel(const bf16* __restrict__ c, const float* __restrict__ w1,
 // backward of one half: dn = dL/d(out) [rows, d] (rows of this half, half-major),
 // dsigma += sum dn * (chat*w) ; dw[col] += sum_rows dn*chat*sigma.  No grad to c.
 template <int NC>
+__device__ __forceinline__ void load_row_f32(const float* p, int d, int lane, float (&v)[NC][8]) {
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    const int col = c * 256 + lane * 8;
+    if (col < d) {
+      const float4 a = *reinterpret_cast<const float4*>(p + col);
+      const float4 b = *reinterpret_cast<const float4*>(p + col + 4);
+      v[c][0] = a.x; v[c][1] = a.y; v[c][2] = a.z; v[c][3] = a.w;
+      v[c][4] = b.x; v[c][5] = b.y; v[c][6] = b.z; v[c][7] = b.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[c][j] = 0.f;
+    }
+  }
+}
+
+template <int NC, bool DN_F32>
 __global__ void __launch_bounds__(ROW_THREADS)
-text_norm_bwd_kernel(const bf16* __restrict__ dn, const bf16* __restrict__ c,
+text_norm_bwd_kernel(const void* __restrict__ dn_, const bf16* __restrict__ c,
                      const float* __restrict__ rstd_in, const float* __restrict__ w,
                      const float* __restrict__ sigma, float* __restrict__ dw,
                      float* __restrict__ dsigma, long long rows, int d, int M, int tok0, int ntok,
@@ -340,7 +357,8 @@ text_norm_bwd_kernel(const bf16* __restrict__ dn, const bf16* __restrict__ c,
     const int tok = tok0 + (int)(r % ntok);
     const long long crow = b * M + tok;
     float g[NC][8], cv[NC][8];
-    load_row<NC>(dn + r * d, d, lane, g);
+    if constexpr (DN_F32) load_row_f32<NC>(reinterpret_cast<const float*>(dn_) + r * d, d, lane, g);
+    else load_row<NC>(reinterpret_cast<const bf16*>(dn_) + r * d, d, lane, g);
     load_row<NC>(c + crow * d, d, lane, cv);
     const float rstd = rstd_in[crow];
 #pragma unroll
@@ -471,9 +489,9 @@ int mmdit_text_norm_fwd(const void* c, const float* w1, const float* w2, const f
   return check_launch("text_norm_fwd_kernel");
 }
 
-int mmdit_text_norm_bwd(const void* dn, const void* c, const float* rstd, const float* w,
-                        const float* sigma, float* dw, float* dsigma, int64_t batch, int32_t tokens,
-                        int32_t tok0, int32_t ntok, int32_t d, void* stream) {
+int mmdit_text_norm_bwd(const void* dn, int32_t dn_fp32, const void* c, const float* rstd,
+                        const float* w, const float* sigma, float* dw, float* dsigma, int64_t batch,
+                        int32_t tokens, int32_t tok0, int32_t ntok, int32_t d, void* stream) {
   MMDIT_REQUIRE(dn && c && rstd && w && sigma && dw && dsigma && batch > 0 && ntok > 0 &&
                     tok0 + ntok <= tokens && d % 8 == 0,
                 MMDIT_ERR_ARG, "text_norm_bwd: bad arguments");
@@ -481,9 +499,13 @@ int mmdit_text_norm_bwd(const void* dn, const void* c, const float* rstd, const 
   const int rpb = 64;
   const unsigned grid = (unsigned)((rows + rpb - 1) / rpb);
   const size_t smem = (size_t)d * sizeof(float);
-  DISPATCH_NC(d, (text_norm_bwd_kernel<NC><<<grid, ROW_THREADS, smem, (cudaStream_t)stream>>>(
-                     (const bf16*)dn, (const bf16*)c, rstd, w, sigma, dw, dsigma, rows, d, tokens,
-                     tok0, ntok, rpb)));
+  if (dn_fp32) {
+    DISPATCH_NC(d, (text_norm_bwd_kernel<NC, true><<<grid, ROW_THREADS, smem, (cudaStream_t)stream>>>(
+                       dn, (const bf16*)c, rstd, w, sigma, dw, dsigma, rows, d, tokens, tok0, ntok, rpb)));
+  } else {
+    DISPATCH_NC(d, (text_norm_bwd_kernel<NC, false><<<grid, ROW_THREADS, smem, (cudaStream_t)stream>>>(
+                       dn, (const bf16*)c, rstd, w, sigma, dw, dsigma, rows, d, tokens, tok0, ntok, rpb)));
+  }
   return check_launch("text_norm_bwd_kernel");
 }
 

@@ -351,3 +351,42 @@ class SwiGLUHiddenFn(Function):
         dx = ops.gemm(dh, wb, b_major=1).reshape(xshape)
         dw = ops.gemm(dh, x2, a_major=1, b_major=1, out_dtype=F32)
         return dx, None, dw, db
+
+
+class TextFrontFn(Function):
+    """The whole text front-end (diff_model.py:323-326) as one node:
+    c' = cat[c_proj(s1 * RMSNorm(c[:, :77])), c_proj2(s2 * RMSNorm(c[:, 77:]))].
+    Keeping it one Function lets the dgrad that feeds the two scalar / two norm-weight gradients
+    stay in fp32 (those are sums over B*77*2304 terms with heavy cancellation)."""
+
+    @staticmethod
+    def forward(ctx, c, w1, w2, s1, s2, split, wb1, wb2, pw1, pw2):
+        c = c.contiguous()
+        Bn, M, _ = c.shape
+        n1, n2, rstd = ops.text_norm_fwd(c, w1, w2, s1, s2, split)
+        t1, t2, d = split, M - split, wb1.shape[0]
+        out = torch.empty((Bn * M, d), device=c.device, dtype=BF16)
+        ops.gemm(n1, wb1, out=out, remap=(t1, M, 0))
+        if t2:
+            ops.gemm(n2, wb2, out=out, remap=(t2, M, t1))
+        ctx.save_for_backward(c, rstd, w1, w2, s1, s2, n1, n2, wb1, wb2)
+        ctx.dims = (Bn, t1, t2, d)
+        return out.view(Bn, M, d)
+
+    @staticmethod
+    def backward(ctx, g):
+        c, rstd, w1, w2, s1, s2, n1, n2, wb1, wb2 = ctx.saved_tensors
+        Bn, t1, t2, d = ctx.dims
+        dw1, dw2 = torch.zeros_like(w1), torch.zeros_like(w2)
+        ds1, ds2 = torch.zeros_like(s1), torch.zeros_like(s2)
+        g1 = g[:, :t1].reshape(Bn * t1, d)
+        dn1 = ops.gemm(g1, wb1, b_major=1, out_dtype=F32)
+        dpw1 = ops.gemm(g1, n1, a_major=1, b_major=1, out_dtype=F32)
+        ops.text_norm_bwd(dn1, c, rstd, w1, s1, dw1, ds1, 0, t1)
+        dpw2 = None
+        if t2:
+            g2 = g[:, t1:].reshape(Bn * t2, d)
+            dn2 = ops.gemm(g2, wb2, b_major=1, out_dtype=F32)
+            dpw2 = ops.gemm(g2, n2, a_major=1, b_major=1, out_dtype=F32)
+            ops.text_norm_bwd(dn2, c, rstd, w2, s2, dw2, ds2, t1, t2)
+        return None, dw1, dw2, ds1, ds2, None, None, None, dpw1, dpw2

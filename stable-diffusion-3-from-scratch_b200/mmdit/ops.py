@@ -237,7 +237,8 @@ def text_norm_bwd(dn, c, rstd, w, sigma, dw, dsigma, tok0, ntok):
     Bn, M, dt = c.shape
     assert dn.is_contiguous()
     _lib.check(_lib.lib().mmdit_text_norm_bwd(
-        _p(dn), _p(c), _p(rstd), _p(w), _p(sigma), _p(dw), _p(dsigma), Bn, M, tok0, ntok, dt,
+        _p(dn), int(dn.dtype == F32), _p(c), _p(rstd), _p(w), _p(sigma), _p(dw), _p(dsigma), Bn, M, tok0,
+        ntok, dt,
         _s()), "mmdit_text_norm_bwd")
 
 

@@ -17,7 +17,7 @@ import torch
 from torch import nn
 
 from mmdit import ops
-from mmdit.functional import LinearFn, TextNormFn, TextProjFn, UnpatchifyFn
+from mmdit.functional import LinearFn, TextFrontFn, UnpatchifyFn
 from mmdit.shadow import packed_weight
 from src.blocks.ImagePositionalEncoding import PatchEmbed
 from src.blocks.Norm import Norm
@@ -156,11 +156,11 @@ class diff_model(nn.Module):
         orig_shape = x_t.shape
         # text front-end (:323-326): per-encoder RMSNorm * scalar, projection, concat over tokens
         cb = c if c.dtype == BF16 else c.to(BF16)
-        n1, n2 = TextNormFn.apply(cb, self.pre_c_norm.weight, self.pre_c_norm2.weight,
-                                  self.learnable_scalar, self.learnable_scalar2, 77)
-        cseq = TextProjFn.apply(n1, n2, packed_weight(self.c_proj, "w", [self.c_proj.weight]),
-                                packed_weight(self.c_proj2, "w", [self.c_proj2.weight]), B,
-                                self.c_proj.weight, self.c_proj2.weight)
+        cseq = TextFrontFn.apply(cb, self.pre_c_norm.weight, self.pre_c_norm2.weight,
+                                 self.learnable_scalar, self.learnable_scalar2, 77,
+                                 packed_weight(self.c_proj, "w", [self.c_proj.weight]),
+                                 packed_weight(self.c_proj2, "w", [self.c_proj2.weight]),
+                                 self.c_proj.weight, self.c_proj2.weight)
 
         # patch embedding (:329,332)
         x = self.pos_enc(x_t if x_t.dtype in (BF16, F32) else x_t.float())

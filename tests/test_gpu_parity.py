@@ -191,3 +191,32 @@ def test_fused_adamw_matches_torch_adamw_and_refreshes_shadows(dev):
         assert float((a - b).abs().max()) <= 2e-6 + 1e-5 * float(b.abs().max())
     assert torch.equal(packed_weight(lin[0], "w", [lin[0].weight]), lin[0].weight.detach().bfloat16())
     assert packed_weight(lin[0], "w", [lin[0].weight]).data_ptr() == wb.data_ptr()
+
+
+@pytest.mark.parametrize("name", ["wide", "px512"])
+def test_model_other_baseline_shapes_vs_oracle(dev, golden, name):
+    """Width-1536 (BASELINE configs[2]/[3]) and 1024+256-token (512 px) shapes.  Forward within 2e-2,
+    loss within 1e-3 of the oracle AND of the reference's fp32 loss (golden); every gradient within
+    max(5e-2, 3 x the reference's own bf16-autocast L2 error on that tensor) in relative L2 norm."""
+    g = golden(name)
+    cfg = g["config"]
+    m, P, v, vo, loss, lo, _ = _run_model(cfg["model"], cfg["B"], cfg["h"], cfg["w"], cfg["M"], dev)
+    assert abs(loss - lo) <= 1e-3 and abs(loss - g["loss_fp32"]) <= 1e-3
+    assert float((v.float() - vo).abs().max() / vo.abs().max()) <= 2e-2
+    for k, p in m.named_parameters():
+        if not p.requires_grad:
+            continue
+        go = P[k].grad
+        n = float(go.norm())
+        if n == 0.0:
+            assert float(p.grad.abs().max()) == 0.0, k
+            continue
+        err = float((p.grad - go).norm()) / n
+        tol = max(5e-2, 3 * g["grad_l2err_bf16"][k])
+        if p.numel() == 1:
+            # one-element parameters (learnable_scalar*, time_scale) are sums of ~1e7 bf16-noisy terms
+            # that nearly cancel; the reference's own bf16-autocast run is 0.14 off its fp32 run on
+            # `learnable_scalar` at depth 3 / dim 768 (measured with oracle/make_golden.py's ref_step)
+            tol = max(tol, 0.2)
+        assert err <= tol, (k, err, g["grad_l2err_bf16"][k])
+        assert abs(n - g["gradnorm_fp32"][k]) <= 2e-2 * n + 1e-9, k      # oracle ~ reference fp32 (its attention core is bf16)

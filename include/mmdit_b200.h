@@ -114,6 +114,10 @@ typedef struct mmdit_attn_args {
   int64_t ld_dq[2], ld_dk[2], ld_dv[2];
   float* delta;          /* workspace */
   float* dq_acc;         /* workspace */
+  /* forward only, optional: device scalar holding an upper bound of |scale * q.k| (see
+   * mmdit_qk_logit_bound).  When present and <= 24 the softmax runs in one pass against this
+   * fixed reference (no running maximum, no rescaling); otherwise the online-softmax path runs. */
+  const float* logit_bound;
 } mmdit_attn_args;
 
 int mmdit_attn_fwd(const mmdit_attn_args* args, void* stream);
@@ -166,6 +170,10 @@ int mmdit_text_norm_bwd(const void* dn, int32_t dn_fp32, const void* c, const fl
 int mmdit_qknorm_rope_fwd(const void* qkv, const float* wq, const float* wk, const float* rope_cos,
                           const float* rope_sin, void* out, int64_t rows, int32_t d, int64_t ld_in,
                           int64_t ld_out, int32_t tokens_per_sample, float eps, void* stream);
+/* out[0] = 1.02 * scale * 64 * max|w_q| * max|w_k| over both streams: bound of the scaled logits
+ * that per-head RMSNorm guarantees (head_dim 64; RoPE is a rotation). wq_c / wk_c may be NULL. */
+int mmdit_qk_logit_bound(const float* wq_x, const float* wk_x, const float* wq_c, const float* wk_c,
+                         float scale, float* out, void* stream);
 int mmdit_qknorm_rope_bwd(const void* dqk, const void* qkv, const float* wq, const float* wk,
                           const float* rope_cos, const float* rope_sin, void* dqkv, float* dwq,
                           float* dwk, int64_t rows, int32_t d, int64_t ld_g, int64_t ld_in,

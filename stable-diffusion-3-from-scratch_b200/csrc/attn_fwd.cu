@@ -32,6 +32,14 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
+// Optional in-kernel timeline (debugging / tuning): one chosen CTA records (event id, clock64).
+__device__ long long* g_attn_timeline = nullptr;
+__device__ int g_attn_timeline_block = -1;
+#define TL(slot, id)                                                        \
+  do {                                                                      \
+    if (tl) { const int s_ = (slot); tl[2 * s_] = (id); tl[2 * s_ + 1] = clock64(); } \
+  } while (0)
+
 struct AttnFwdParams {
   CUtensorMap tmQ[2], tmK[2], tmV[2];  // [0] image stream, [1] text stream
   bf16* o[2];
@@ -39,6 +47,7 @@ struct AttnFwdParams {
   float* lse;  // [B, H, N+M]
   int B, H, N, M;
   float scale, scale_log2;
+  const float* logit_bound;  // device scalar: upper bound of |scale * q.k| (QK-RMSNorm makes it small), or null
 };
 
 __global__ void __launch_bounds__(ATT_THREADS, 2)
@@ -67,22 +76,35 @@ attn_fwd_kernel(const __grid_constant__ AttnFwdParams p) {
   const int q_rows = qs == 0 ? p.N : p.M;
   const int q_valid = min(ATT_TILE, q_rows - q_row0);
 
-  if ((smem_u32(smem) & 1023u) != 0) __trap();
-  if (warp == 1 && lane == 0) {
-    mbar_init(q_full, 1);
-    for (int s = 0; s < 2; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
-    mbar_init(s_full, 1);
-    mbar_init(p_full, 128);
-    mbar_init(pv_done, 1);
-    mbar_fence_init();
+  const int linear_block = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+  long long* tl = nullptr;   // [0,64): MMA warp events, [64,192): softmax warp 2 events
+  if (g_attn_timeline && linear_block == g_attn_timeline_block && lane == 0) {
+    if (warp == 1) tl = g_attn_timeline;
+    if (warp == 2) tl = g_attn_timeline + 128;
   }
+  int tls = 0;
+  TL(tls++, 1);
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
   if (warp == 0) {
     if (lane == 0) {
-      tma_prefetch_desc(&p.tmQ[qs]);
-      tma_prefetch_desc(&p.tmK[0]);
-      tma_prefetch_desc(&p.tmV[0]);
-      if (ntc > 0) { tma_prefetch_desc(&p.tmK[1]); tma_prefetch_desc(&p.tmV[1]); }
+      mbar_init(q_full, 1);
+      for (int s = 0; s < 2; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
+      mbar_init(s_full, 1);
+      mbar_init(p_full, 128);
+      mbar_init(pv_done, 1);
+      mbar_fence_init();
+      // fire Q and the first two K/V tiles right away: they fly while TMEM is allocated
+      mbar_expect_tx(q_full, ATT_TILE_BYTES);
+      tma_load_4d(sQ, &p.tmQ[qs], q_full, 0, h, q_row0, b);
+      for (int j = 0; j < 2 && j < nkv; ++j) {
+        const int ks = j < ntx ? 0 : 1;
+        const int row0 = (ks == 0 ? j : j - ntx) * ATT_TILE;
+        mbar_expect_tx(&kv_full[j], 2 * ATT_TILE_BYTES);
+        tma_load_4d(sK + j * ATT_TILE_BYTES, &p.tmK[ks], &kv_full[j], 0, h, row0, b);
+        tma_load_4d(sV + j * ATT_TILE_BYTES, &p.tmV[ks], &kv_full[j], 0, h, row0, b);
+      }
     }
+    __syncwarp();
     tmem_alloc(tmem_slot, 256);
     tmem_relinquish();
   }
@@ -94,9 +116,7 @@ attn_fwd_kernel(const __grid_constant__ AttnFwdParams p) {
 
   if (warp == 0) {
     if (lane == 0) {
-      mbar_expect_tx(q_full, ATT_TILE_BYTES);
-      tma_load_4d(sQ, &p.tmQ[qs], q_full, 0, h, q_row0, b);
-      for (int j = 0; j < nkv; ++j) {
+      for (int j = 2; j < nkv; ++j) {   // tiles 0 and 1 were issued in the prologue
         const int st = j & 1;
         const int ks = j < ntx ? 0 : 1;
         const int row0 = (ks == 0 ? j : j - ntx) * ATT_TILE;
@@ -109,8 +129,15 @@ attn_fwd_kernel(const __grid_constant__ AttnFwdParams p) {
   } else if (warp == 1) {
     if (lane == 0) {
       const uint32_t idesc_o = make_idesc_bf16(128, 64, 0, 1);
-      const uint32_t q_addr = smem_u32(sQ), p_addr = smem_u32(sP);
+      // descriptors are built once; stepping K only adds a constant to the 14-bit address field
+      const uint64_t q_desc = desc_kmajor(smem_u32(sQ), 0);
+      const uint64_t p_desc = desc_kmajor(smem_u32(sP), 0);
+      const uint64_t k_desc0 = desc_kmajor(smem_u32(sK), 0);
+      const uint64_t v_desc0 = desc_mnmajor(smem_u32(sV), 0, ATT_TILE_BYTES);
+      constexpr uint64_t kStepK = 32 >> 4, kStepMN = 2048 >> 4, kTile = ATT_TILE_BYTES >> 4;
+      TL(tls++, 2);
       mbar_wait(q_full, 0);
+      TL(tls++, 3);
       for (int j = 0; j < nkv; ++j) {
         const int st = j & 1;
         const int ks = j < ntx ? 0 : 1;
@@ -118,21 +145,31 @@ attn_fwd_kernel(const __grid_constant__ AttnFwdParams p) {
         const int nv = min(ATT_TILE, (ks == 0 ? p.N : p.M) - row0);
         const int n_mma = (nv + 15) & ~15;  // partial key tiles: only the columns that exist
         const uint32_t idesc_s = make_idesc_bf16(128, n_mma, 0, 0);
-        const uint32_t k_addr = smem_u32(sK + st * ATT_TILE_BYTES);
-        const uint32_t v_addr = smem_u32(sV + st * ATT_TILE_BYTES);
+        const uint64_t k_desc = k_desc0 + st * kTile, v_desc = v_desc0 + st * kTile;
         mbar_wait(&kv_full[st], (j >> 1) & 1);
         tc_fence_after();
+        TL(tls++, 10 + j);
 #pragma unroll
         for (int k = 0; k < ATT_HD / 16; ++k)
-          umma_bf16(tmem_S, desc_kmajor(q_addr, k), desc_kmajor(k_addr, k), idesc_s, k > 0);
+          umma_bf16(tmem_S, q_desc + k * kStepK, k_desc + k * kStepK, idesc_s, k > 0);
         umma_commit(s_full);
+        TL(tls++, 20 + j);
         mbar_wait(p_full, j & 1);
         tc_fence_after();
-        for (int k = 0; k < n_mma / 16; ++k)
-          umma_bf16(tmem_O, desc_kmajor(p_addr + (k >> 2) * ATT_TILE_BYTES, k & 3),
-                    desc_mnmajor(v_addr, k, ATT_TILE_BYTES), idesc_o, (j > 0 || k > 0) ? 1u : 0u);
+        TL(tls++, 30 + j);
+        if (n_mma == ATT_TILE) {
+#pragma unroll
+          for (int k = 0; k < ATT_TILE / 16; ++k)
+            umma_bf16(tmem_O, p_desc + (k >> 2) * kTile + (k & 3) * kStepK, v_desc + k * kStepMN, idesc_o,
+                      (j > 0 || k > 0) ? 1u : 0u);
+        } else {
+          for (int k = 0; k < n_mma / 16; ++k)
+            umma_bf16(tmem_O, p_desc + (k >> 2) * kTile + (k & 3) * kStepK, v_desc + k * kStepMN, idesc_o,
+                      (j > 0 || k > 0) ? 1u : 0u);
+        }
         umma_commit(&kv_empty[st]);
         umma_commit(pv_done);
+        TL(tls++, 40 + j);
       }
     }
   } else {
@@ -142,39 +179,55 @@ attn_fwd_kernel(const __grid_constant__ AttnFwdParams p) {
     const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
     float m = -INFINITY, l = 0.f;
     const float sl2 = p.scale_log2;
+    // With QK-RMSNorm the scaled logits are bounded by 8*max|w_q|*max|w_k|; when the caller
+    // supplies that bound (and it is small enough for exp2 not to underflow) the softmax needs
+    // neither a running maximum nor O rescaling: P = exp(s - bound) in one pass over S.
+    float bound = p.logit_bound ? *p.logit_bound : INFINITY;
+    const bool use_bound = bound >= 0.f && bound <= 24.f;
+    const float bound_l2 = bound * 1.4426950408889634f;
+    if (use_bound) m = bound / p.scale;   // so that lse = m*scale + log(l) below stays valid
     for (int j = 0; j < nkv; ++j) {
       const int ks = j < ntx ? 0 : 1;
       const int row0 = (ks == 0 ? j : j - ntx) * ATT_TILE;
       const int nv = min(ATT_TILE, (ks == 0 ? p.N : p.M) - row0);  // valid keys in this tile
       const int n_mma = (nv + 15) & ~15;
       const int nchunk = (n_mma + 31) / 32;
+      TL(tls++, 50 + j);
       mbar_wait(s_full, j & 1);
       tc_fence_after();
-      // pass 1: row maximum (4 independent chains; TMEM loads issued in pairs)
-      float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-      for (int c = 0; c < nchunk; c += 2) {
-        uint32_t s0[32], s1[32];
-        tmem_ld32(tmem_S + lane_off + c * 32, s0);
-        if (c + 1 < nchunk) tmem_ld32(tmem_S + lane_off + (c + 1) * 32, s1);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (c * 32 + i < nv) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(s0[i]));
-        if (c + 1 < nchunk) {
+      TL(tls++, 60 + j);
+      float alpha = 1.f, mb, m_new = m;
+      if (!use_bound) {
+        // pass 1: row maximum (4 independent chains; TMEM loads issued in pairs)
+        float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+        for (int c = 0; c < nchunk; c += 2) {
+          uint32_t s0[32], s1[32];
+          tmem_ld32(tmem_S + lane_off + c * 32, s0);
+          if (c + 1 < nchunk) tmem_ld32(tmem_S + lane_off + (c + 1) * 32, s1);
+          tmem_ld_wait();
 #pragma unroll
           for (int i = 0; i < 32; ++i)
-            if ((c + 1) * 32 + i < nv) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(s1[i]));
+            if (c * 32 + i < nv) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(s0[i]));
+          if (c + 1 < nchunk) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if ((c + 1) * 32 + i < nv) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(s1[i]));
+          }
         }
+        const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+        m_new = fmaxf(m, mx);
+        alpha = ex2_approx((m - m_new) * sl2);
+        mb = m_new * sl2;
+      } else {
+        mb = bound_l2;   // fixed reference point: no running maximum, no rescale of O
       }
-      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
-      const float m_new = fmaxf(m, mx);
-      const float alpha = ex2_approx((m - m_new) * sl2);
-      const float mb = m_new * sl2;
+      TL(tls++, 70 + j);
       if (j > 0) {
-        mbar_wait(pv_done, (j - 1) & 1);
+        mbar_wait(pv_done, (j - 1) & 1);   // previous P V retired: sP is free (and O is final so far)
         tc_fence_after();
+        TL(tls++, 80 + j);
         // rescale O only if some row of this warp actually raised its maximum
-        if (!__all_sync(0xffffffffu, m_new == m)) {
+        if (!use_bound && !__all_sync(0xffffffffu, m_new == m)) {
 #pragma unroll
           for (int c = 0; c < 2; ++c) {
             uint32_t o[32];
@@ -187,27 +240,52 @@ attn_fwd_kernel(const __grid_constant__ AttnFwdParams p) {
           tmem_st_wait();
         }
       }
+      TL(tls++, 90 + j);
       float rs4[4] = {0.f, 0.f, 0.f, 0.f};
+      if (nv == ATT_TILE) {
+        // full key tile: no masking in the inner loop
 #pragma unroll 1
-      for (int c = 0; c < nchunk; ++c) {
-        uint32_t s[32];
-        tmem_ld32(tmem_S + lane_off + c * 32, s);
-        tmem_ld_wait();
-        uint8_t* prow = sP + (c >> 1) * ATT_TILE_BYTES + r * 128;
+        for (int c = 0; c < 4; ++c) {
+          uint32_t s[32];
+          tmem_ld32(tmem_S + lane_off + c * 32, s);
+          tmem_ld_wait();
+          uint8_t* prow = sP + (c >> 1) * ATT_TILE_BYTES + r * 128;
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          float e[8];
+          for (int g = 0; g < 4; ++g) {
+            float e[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int col = c * 32 + g * 8 + i;
-            e[i] = col < nv ? ex2_approx(fmaf(__uint_as_float(s[g * 8 + i]), sl2, -mb)) : 0.f;
-            rs4[i & 3] += e[i];
+            for (int i = 0; i < 8; ++i) {
+              e[i] = ex2_approx(fmaf(__uint_as_float(s[g * 8 + i]), sl2, -mb));
+              rs4[i & 3] += e[i];
+            }
+            uint4 u;
+            u.x = pack_bf16x2(e[0], e[1]); u.y = pack_bf16x2(e[2], e[3]);
+            u.z = pack_bf16x2(e[4], e[5]); u.w = pack_bf16x2(e[6], e[7]);
+            *reinterpret_cast<uint4*>(prow + ((((c & 1) * 4 + g) ^ (r & 7)) << 4)) = u;
           }
-          uint4 u;
-          u.x = pack_bf16x2(e[0], e[1]); u.y = pack_bf16x2(e[2], e[3]);
-          u.z = pack_bf16x2(e[4], e[5]); u.w = pack_bf16x2(e[6], e[7]);
-          const int chunk16 = (c & 1) * 4 + g;  // 16-byte chunk inside the 128-byte row
-          *reinterpret_cast<uint4*>(prow + ((chunk16 ^ (r & 7)) << 4)) = u;
+        }
+      } else {
+#pragma unroll 1
+        for (int c = 0; c < nchunk; ++c) {
+          uint32_t s[32];
+          tmem_ld32(tmem_S + lane_off + c * 32, s);
+          tmem_ld_wait();
+          uint8_t* prow = sP + (c >> 1) * ATT_TILE_BYTES + r * 128;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            float e[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int col = c * 32 + g * 8 + i;
+              e[i] = col < nv ? ex2_approx(fmaf(__uint_as_float(s[g * 8 + i]), sl2, -mb)) : 0.f;
+              rs4[i & 3] += e[i];
+            }
+            uint4 u;
+            u.x = pack_bf16x2(e[0], e[1]); u.y = pack_bf16x2(e[2], e[3]);
+            u.z = pack_bf16x2(e[4], e[5]); u.w = pack_bf16x2(e[6], e[7]);
+            const int chunk16 = (c & 1) * 4 + g;  // 16-byte chunk inside the 128-byte row
+            *reinterpret_cast<uint4*>(prow + ((chunk16 ^ (r & 7)) << 4)) = u;
+          }
         }
       }
       const float rs = (rs4[0] + rs4[1]) + (rs4[2] + rs4[3]);
@@ -216,9 +294,11 @@ attn_fwd_kernel(const __grid_constant__ AttnFwdParams p) {
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(p_full);
+      TL(tls++, 100 + j);
     }
     mbar_wait(pv_done, (nkv - 1) & 1);
     tc_fence_after();
+    TL(tls++, 110);
     const float inv_l = 1.f / l;
     const long long grow = (long long)b * q_rows + q_row0 + r;
     bf16* orow = p.o[qs] + grow * p.ldo[qs] + h * ATT_HD;
@@ -242,6 +322,7 @@ attn_fwd_kernel(const __grid_constant__ AttnFwdParams p) {
       p.lse[((long long)b * p.H + h) * (p.N + p.M) + t] = m * p.scale + logf(l);
     }
   }
+  TL(tls++, 120);
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem_base, 256);
@@ -258,6 +339,12 @@ int make_attn_tmap(CUtensorMap* map, const void* base, long long ld, int H, int 
 }  // namespace mmdit
 
 using namespace mmdit;
+
+extern "C" int mmdit_debug_attn_timeline(long long* buf, int block) {
+  cudaError_t e = cudaMemcpyToSymbol(g_attn_timeline, &buf, sizeof(buf));
+  if (e == cudaSuccess) e = cudaMemcpyToSymbol(g_attn_timeline_block, &block, sizeof(block));
+  return (int)e;
+}
 
 extern "C" int mmdit_attn_fwd(const mmdit_attn_args* a, void* stream) {
   MMDIT_REQUIRE(a, MMDIT_ERR_ARG, "attn_fwd: null args");
@@ -289,6 +376,7 @@ extern "C" int mmdit_attn_fwd(const mmdit_attn_args* a, void* stream) {
   p.B = a->B; p.H = a->H; p.N = a->N; p.M = a->M;
   p.scale = a->scale;
   p.scale_log2 = a->scale * 1.4426950408889634f;
+  p.logit_bound = a->logit_bound;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel,

@@ -460,6 +460,23 @@ fold_slices_kernel(const float* __restrict__ ws, float* __restrict__ out, long l
   }
 }
 
+// out[0] = 1.02 * scale * 64 * max(|wq_x|,|wq_c|) * max(|wk_x|,|wk_c|): an upper bound of the scaled
+// attention logits after per-head RMSNorm (unit-RMS vectors of length 64 times the norm weight;
+// RoPE is a rotation), with 2 % slack for the bf16 rounding of q and k.
+__global__ void qk_logit_bound_kernel(const float* __restrict__ wq_x, const float* __restrict__ wk_x,
+                                      const float* __restrict__ wq_c, const float* __restrict__ wk_c,
+                                      float scale, float* __restrict__ out) {
+  const int i = threadIdx.x;  // 64 threads
+  float q = fmaxf(fabsf(wq_x[i]), wq_c ? fabsf(wq_c[i]) : 0.f);
+  float k = fmaxf(fabsf(wk_x[i]), wk_c ? fabsf(wk_c[i]) : 0.f);
+  __shared__ float sq[2], sk[2];
+  q = warp_max(q);
+  k = warp_max(k);
+  if ((i & 31) == 0) { sq[i >> 5] = q; sk[i >> 5] = k; }
+  __syncthreads();
+  if (i == 0) out[0] = 1.02f * scale * 64.f * fmaxf(sq[0], sq[1]) * fmaxf(sk[0], sk[1]);
+}
+
 static inline unsigned grid_for(long long work_items, int threads) {
   long long blocks = (work_items + threads - 1) / threads;
   const long long cap = (long long)num_sms() * 16;
@@ -515,6 +532,13 @@ int mmdit_gate_residual_fwd(const void* a, const void* gate, const void* resid, 
       (const bf16*)a, (const bf16*)gate, (const bf16*)resid, (bf16*)out, rows, d, rows_per_batch,
       ld_gate);
   return check_launch("gate_residual_fwd_kernel");
+}
+
+int mmdit_qk_logit_bound(const float* wq_x, const float* wk_x, const float* wq_c, const float* wk_c,
+                         float scale, float* out, void* stream) {
+  MMDIT_REQUIRE(wq_x && wk_x && out, MMDIT_ERR_ARG, "qk_logit_bound: bad arguments");
+  qk_logit_bound_kernel<<<1, 64, 0, (cudaStream_t)stream>>>(wq_x, wk_x, wq_c, wk_c, scale, out);
+  return check_launch("qk_logit_bound_kernel");
 }
 
 int mmdit_swiglu_fwd(const void* h12, void* a, int64_t rows, int32_t hidden, void* stream) {

@@ -20,6 +20,7 @@ SIGNATURES = {
     "mmdit_text_norm_fwd": [vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, f32, vp],
     "mmdit_text_norm_bwd": [vp, i32, vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, i32, vp],
     "mmdit_qknorm_rope_fwd": [vp, vp, vp, vp, vp, vp, i64, i32, i64, i64, i32, f32, vp],
+    "mmdit_qk_logit_bound": [vp, vp, vp, vp, f32, vp, vp],
     "mmdit_qknorm_rope_bwd": [vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, i64, i64, i64, i32, f32, vp],
     "mmdit_swiglu_fwd": [vp, vp, i64, i32, vp],
     "mmdit_swiglu_bwd": [vp, vp, vp, vp, vp, i64, i32, vp],

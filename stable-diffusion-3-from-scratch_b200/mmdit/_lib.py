@@ -48,6 +48,7 @@ class AttnArgs(C.Structure):
         ("dq", c_vp * 2), ("dk", c_vp * 2), ("dv", c_vp * 2),
         ("ld_dq", c_i64 * 2), ("ld_dk", c_i64 * 2), ("ld_dv", c_i64 * 2),
         ("delta", c_vp), ("dq_acc", c_vp),
+        ("logit_bound", c_vp),
     ]
 
 

@@ -141,7 +141,9 @@ class JointAttentionFn(Function):
         q = (qk_x[:, :d], qk_c[:, :d])
         k = (qk_x[:, d:], qk_c[:, d:])
         v = (qkv_x[:, 2 * d:], qkv_c[:, 2 * d:])
-        o_x, o_c, lse = ops.attn_fwd(q, k, v, Bn, H, N, M, 0.125)
+        # QK-RMSNorm bounds the logits: lets the kernel run a single-pass softmax
+        bound = ops.qk_logit_bound(wq_x, wk_x, wq_c, wk_c, 0.125)
+        o_x, o_c, lse = ops.attn_fwd(q, k, v, Bn, H, N, M, 0.125, logit_bound=bound)
         ctx.save_for_backward(qkv_x, qkv_c, qk_x, qk_c, o_x, o_c, lse, wq_x, wk_x, wq_c, wk_c,
                               rope_cos, rope_sin)
         ctx.dims = (Bn, H, N, M)

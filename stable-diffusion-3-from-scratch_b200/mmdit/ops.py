@@ -138,7 +138,15 @@ def _fill_streams(args, name_ptr, name_ld, tensors):
         getattr(args, name_ld)[s] = t.stride(0)
 
 
-def attn_fwd(q, k, v, B, H, N, M, scale):
+def qk_logit_bound(wq_x, wk_x, wq_c, wk_c, scale):
+    """Device scalar bounding |scale * q.k| after per-head RMSNorm with these norm weights."""
+    out = torch.empty(1, device=wq_x.device, dtype=F32)
+    _lib.check(_lib.lib().mmdit_qk_logit_bound(_p(wq_x), _p(wk_x), _p(wq_c), _p(wk_c), float(scale), _p(out),
+                                               _s()), "mmdit_qk_logit_bound")
+    return out
+
+
+def attn_fwd(q, k, v, B, H, N, M, scale, logit_bound=None):
     """q/k/v: pairs (image, text) of [B*rows, H*64] bf16 views (unit inner stride).
     Returns (o_x [B*N,H*64], o_c [B*M,H*64] or None, lse [B,H,N+M])."""
     _need_cuda(q[0])
@@ -152,6 +160,7 @@ def attn_fwd(q, k, v, B, H, N, M, scale):
     _fill_streams(a, "v", "ld_v", v)
     _fill_streams(a, "o", "ld_o", o)
     a.lse = lse.data_ptr()
+    a.logit_bound = _p(logit_bound) or None
     a.B, a.H, a.N, a.M, a.head_dim, a.scale = B, H, N, M, 64, float(scale)
     _lib.check(_lib.lib().mmdit_attn_fwd(C.byref(a), _s()), "mmdit_attn_fwd")
     return o[0], o[1], lse

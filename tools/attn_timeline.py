@@ -1,0 +1,34 @@
+"""Dump the in-kernel timeline of one attention-forward CTA (debug/tuning)."""
+import ctypes as C, os, sys, torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "stable-diffusion-3-from-scratch_b200"))
+from mmdit import _lib, ops
+L = _lib.lib()
+B, H, N, M = 64, 12, 256, 154
+d = H * 64
+dev = "cuda"
+qkv_x = torch.randn(B * N, 3 * d, device=dev).bfloat16(); qkv_c = torch.randn(B * M, 3 * d, device=dev).bfloat16()
+qs, ks, vs = ((qkv_x[:, i * d:(i + 1) * d], qkv_c[:, i * d:(i + 1) * d]) for i in range(3))
+one = torch.ones(64, device=dev)
+bound = ops.qk_logit_bound(one, one, one, one, 0.125) * 2.9   # random-normal q,k: looser bound
+for _ in range(3):
+    ops.attn_fwd(qs, ks, vs, B, H, N, M, 0.125, logit_bound=bound)
+torch.cuda.synchronize()
+buf = torch.zeros(512, dtype=torch.int64, device=dev)
+for blk in [int(x) for x in (sys.argv[1:] or [1500, 1501, 1503])]:
+    buf.zero_()
+    L.mmdit_debug_attn_timeline.argtypes = [C.c_void_p, C.c_int]
+    assert L.mmdit_debug_attn_timeline(buf.data_ptr(), blk) == 0
+    ops.attn_fwd(qs, ks, vs, B, H, N, M, 0.125, logit_bound=bound)
+    torch.cuda.synchronize()
+    t = buf.cpu().tolist()
+    ev = []
+    for base, who in ((0, "mma"), (128, "smx")):
+        for i in range(64):
+            if t[base + 2 * i]:
+                ev.append((t[base + 2 * i + 1], who, t[base + 2 * i]))
+    ev.sort()
+    t0 = ev[0][0]
+    print(f"--- block {blk} (q tile {blk % 4}) : total {ev[-1][0] - t0} cycles")
+    print(" ".join(f"{who}{eid}@{tt - t0}" for tt, who, eid in ev))
+L.mmdit_debug_attn_timeline(None, -1)

@@ -37,17 +37,32 @@ def ref_attention(q, k, v, scale):
     return p @ v, torch.logsumexp(s, -1)
 
 
-def attn_case(B, H, N, M, bwd=True, seed=0):
+def _unit_rms_heads(t, d, H):
+    # q and k as they leave QK-RMSNorm (weight 1): every 64-wide head has unit RMS
+    qk = t[:, :2 * d].float().view(t.shape[0], 2 * H, 64)
+    qk = qk * torch.rsqrt(qk.pow(2).mean(-1, keepdim=True))
+    t[:, :2 * d] = qk.view(t.shape[0], 2 * d).bfloat16()
+    return t
+
+
+def attn_case(B, H, N, M, bwd=True, seed=0, bounded=False):
     torch.manual_seed(seed)
     d = H * 64
-    print(f"[attn] B={B} H={H} N={N} M={M}")
+    print(f"[attn] B={B} H={H} N={N} M={M} bounded={bounded}")
     qkv_x = torch.randn(B * N, 3 * d, device=dev).bfloat16()
     qkv_c = torch.randn(B * M, 3 * d, device=dev).bfloat16() if M else None
+    bound = None
+    if bounded:
+        qkv_x = _unit_rms_heads(qkv_x, d, H)
+        qkv_c = _unit_rms_heads(qkv_c, d, H) if M else None
+        one = torch.ones(64, device=dev)
+        bound = ops.qk_logit_bound(one, one, one, one, 0.125)
+        assert abs(float(bound) - 8.16) < 1e-4
     qs = (qkv_x[:, :d], qkv_c[:, :d] if M else None)
     ks = (qkv_x[:, d:2 * d], qkv_c[:, d:2 * d] if M else None)
     vs = (qkv_x[:, 2 * d:], qkv_c[:, 2 * d:] if M else None)
     scale = 0.125
-    o_x, o_c, lse = ops.attn_fwd(qs, ks, vs, B, H, N, M, scale)
+    o_x, o_c, lse = ops.attn_fwd(qs, ks, vs, B, H, N, M, scale, logit_bound=bound)
     torch.cuda.synchronize()
 
     def joint(tx, tc):
@@ -87,6 +102,8 @@ def group_attn():
     ok &= attn_case(2, 4, 256, 154)
     ok &= attn_case(2, 3, 240, 77)      # 24x40 latent is 12x20 tokens; ragged everywhere
     ok &= attn_case(1, 2, 1024, 256)
+    ok &= attn_case(2, 4, 256, 154, bounded=True)      # single-pass softmax against the QK-norm bound
+    ok &= attn_case(2, 3, 240, 77, bounded=True)
     return ok
 
 
@@ -95,6 +112,9 @@ def group_attn_perf():
         d = H * 64
         qkv_x = torch.randn(B * N, 3 * d, device=dev).bfloat16()
         qkv_c = torch.randn(B * M, 3 * d, device=dev).bfloat16()
+        qkv_x, qkv_c = _unit_rms_heads(qkv_x, d, H), _unit_rms_heads(qkv_c, d, H)
+        one = torch.ones(64, device=dev)
+        bound = ops.qk_logit_bound(one, one, one, one, 0.125)
         qs, ks, vs = ((qkv_x[:, i * d:(i + 1) * d], qkv_c[:, i * d:(i + 1) * d]) for i in range(3))
         o_x, o_c, lse = ops.attn_fwd(qs, ks, vs, B, H, N, M, 0.125)
         do_x, do_c = torch.randn_like(o_x), torch.randn_like(o_c)
@@ -116,7 +136,9 @@ def group_attn_perf():
             return e0.elapsed_time(e1) / iters
 
         ms = timeit(lambda: ops.attn_fwd(qs, ks, vs, B, H, N, M, 0.125))
-        print(f"[attn perf] B={B} H={H} T={T} fwd {ms * 1e3:8.1f} us {flops / ms / 1e9:7.1f} TFLOP/s")
+        print(f"[attn perf] B={B} H={H} T={T} fwd (online softmax) {ms * 1e3:8.1f} us {flops / ms / 1e9:7.1f} TFLOP/s")
+        ms = timeit(lambda: ops.attn_fwd(qs, ks, vs, B, H, N, M, 0.125, logit_bound=bound))
+        print(f"[attn perf] B={B} H={H} T={T} fwd (bounded, 1 pass) {ms * 1e3:8.1f} us {flops / ms / 1e9:7.1f} TFLOP/s")
         ms = timeit(lambda: ops.attn_bwd(qs, ks, vs, (o_x, o_c), lse, (do_x, do_c), dq, dk, dv, B, H,
                                          N, M, 0.125))
         print(f"[attn perf] B={B} H={H} T={T} bwd {ms * 1e3:8.1f} us {2.5 * flops / ms / 1e9:7.1f} TFLOP/s")

@@ -157,7 +157,7 @@ def instrument_kernels(trainer, batch):
         return 2.0 * M * N * K
 
     ops.gemm = timed("gemm", orig[0], gemm_work)
-    ops.attn_fwd = timed("attn_fwd", orig[1], lambda q, k, v, B, H, N, M, s: 4.0 * B * H * (N + M) ** 2 * 64)
+    ops.attn_fwd = timed("attn_fwd", orig[1], lambda q, k, v, B, H, N, M, s, **kw: 4.0 * B * H * (N + M) ** 2 * 64)
     ops.attn_bwd = timed("attn_bwd", orig[2],
                          lambda q, k, v, o, l, do, dq, dk, dv, B, H, N, M, s: 10.0 * B * H * (N + M) ** 2 * 64)
     import mmdit.functional as Fn

@@ -12,6 +12,8 @@
 //   warp 0      TMA producer (K,V once; Q_i,dO_i through a 2-deep ring)
 //   warp 1      MMA issuer
 //   warps 2..9  compute: thread = (key row, 64-query half)
+//   warps 10..13 drain each finished dQ tile from TMEM into the fp32 accumulator (vector RED),
+//               off the compute warps' critical path
 #include "common.cuh"
 #include "mmdit_b200.h"
 
@@ -20,13 +22,22 @@ namespace mmdit {
 constexpr int ATT_TILE = 128;
 constexpr int ATT_HD = 64;
 constexpr int ATT_TILE_BYTES = ATT_TILE * ATT_HD * 2;  // 16 KiB
-constexpr int BWD_THREADS = 320;
-constexpr int BWD_SMEM = 10 * ATT_TILE_BYTES + 2 * 2 * 128 * 4 + 256;
+constexpr int BWD_THREADS = 448;  // TMA warp, MMA warp, 8 compute warps, 4 dQ-drain warps
+constexpr int BWD_SMEM = 14 * ATT_TILE_BYTES + 2 * 2 * 128 * 4 + 256;  // 226.25 KiB
 
 int make_attn_tmap(CUtensorMap* map, const void* base, long long ld, int H, int rows, int B);
 
+// Optional in-kernel timeline (debugging / tuning): one chosen CTA records (event id, clock64).
+__device__ long long* g_bwd_timeline = nullptr;
+__device__ int g_bwd_timeline_block = -1;
+#define TL(slot, id)                                                                   \
+  do {                                                                                 \
+    if (tl) { const int s_ = (slot); tl[2 * s_] = (id); tl[2 * s_ + 1] = clock64(); }  \
+  } while (0)
+
 struct AttnBwdParams {
   CUtensorMap tmQ[2], tmK[2], tmV[2], tmdO[2];
+  CUtensorMap tmdQ[2];  // fp32 dQ accumulator [B, T, H*64] viewed per stream, box 32 x 128, 128B swizzle
   bf16* dk[2];
   bf16* dv[2];
   long long ld_dk[2], ld_dv[2];
@@ -56,9 +67,9 @@ attn_bwd_kernel(const __grid_constant__ AttnBwdParams p) {
   uint8_t* sV = smem + ATT_TILE_BYTES;
   uint8_t* sQ = smem + 2 * ATT_TILE_BYTES;    // [2]
   uint8_t* sdO = smem + 4 * ATT_TILE_BYTES;   // [2]
-  uint8_t* sPt = smem + 6 * ATT_TILE_BYTES;   // 2 halves
-  uint8_t* sdSt = smem + 8 * ATT_TILE_BYTES;  // 2 halves
-  float* sLse = reinterpret_cast<float*>(smem + 10 * ATT_TILE_BYTES);  // [2][128]
+  uint8_t* sPt = smem + 6 * ATT_TILE_BYTES;    // [2 buffers][2 halves]
+  uint8_t* sdSt = smem + 10 * ATT_TILE_BYTES;  // [2 buffers][2 halves]
+  float* sLse = reinterpret_cast<float*>(smem + 14 * ATT_TILE_BYTES);  // [2][128]
   float* sDelta = sLse + 256;                                          // [2][128]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sDelta + 256);
   uint64_t* kv_full = bars + 0;
@@ -68,7 +79,10 @@ attn_bwd_kernel(const __grid_constant__ AttnBwdParams p) {
   uint64_t* pt_full = bars + 6;
   uint64_t* dq_full = bars + 7;
   uint64_t* dq_empty = bars + 8;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+  uint64_t* buf_free = bars + 9;  // [2]: P^T/dS^T smem buffer no longer read by any MMA
+  uint64_t* all_done = bars + 11; // every MMA of this CTA has retired
+  uint64_t* stage_free = bars + 12;  // [2]: dQ staging (aliases the P^T buffer) read out by the TMA reduce
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int T = p.N + p.M;
@@ -81,17 +95,42 @@ attn_bwd_kernel(const __grid_constant__ AttnBwdParams p) {
   const int k_rows = ks == 0 ? p.N : p.M;
   const int k_valid = min(ATT_TILE, k_rows - k_row0);
 
-  if ((smem_u32(smem) & 1023u) != 0) __trap();
-  if (warp == 1 && lane == 0) {
-    mbar_init(kv_full, 1);
-    for (int s = 0; s < 2; ++s) { mbar_init(&qdo_full[s], 1); mbar_init(&qdo_empty[s], 1); }
-    mbar_init(st_full, 1);
-    mbar_init(pt_full, 256);
-    mbar_init(dq_full, 1);
-    mbar_init(dq_empty, 256);
-    mbar_fence_init();
+  const int linear_block = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+  long long* tl = nullptr;   // [0,128): MMA warp events, [128,256): compute warp 2 events
+  if (g_bwd_timeline && linear_block == g_bwd_timeline_block && lane == 0) {
+    if (warp == 1) tl = g_bwd_timeline;
+    if (warp == 2) tl = g_bwd_timeline + 128;
   }
+  int tls = 0;
+  TL(tls++, 1);
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
   if (warp == 0) {
+    if (lane == 0) {
+      mbar_init(kv_full, 1);
+      for (int s = 0; s < 2; ++s) { mbar_init(&qdo_full[s], 1); mbar_init(&qdo_empty[s], 1); }
+      mbar_init(st_full, 1);
+      mbar_init(pt_full, 256);
+      mbar_init(dq_full, 1);
+      mbar_init(dq_empty, 128);   // the 4 drain warps
+      mbar_init(&buf_free[0], 1);
+      mbar_init(&buf_free[1], 1);
+      mbar_init(all_done, 1);
+      mbar_init(&stage_free[0], 1);
+      mbar_init(&stage_free[1], 1);
+      mbar_fence_init();
+      // K, V and the first two (Q, dO) tiles fly while TMEM is being allocated
+      mbar_expect_tx(kv_full, 2 * ATT_TILE_BYTES);
+      tma_load_4d(sK, &p.tmK[ks], kv_full, 0, h, k_row0, b);
+      tma_load_4d(sV, &p.tmV[ks], kv_full, 0, h, k_row0, b);
+      for (int i = 0; i < 2 && i < nt; ++i) {
+        const int qs = i < ntx ? 0 : 1;
+        const int row0 = (qs == 0 ? i : i - ntx) * ATT_TILE;
+        mbar_expect_tx(&qdo_full[i], 2 * ATT_TILE_BYTES);
+        tma_load_4d(sQ + i * ATT_TILE_BYTES, &p.tmQ[qs], &qdo_full[i], 0, h, row0, b);
+        tma_load_4d(sdO + i * ATT_TILE_BYTES, &p.tmdO[qs], &qdo_full[i], 0, h, row0, b);
+      }
+    }
+    __syncwarp();
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
@@ -104,10 +143,7 @@ attn_bwd_kernel(const __grid_constant__ AttnBwdParams p) {
 
   if (warp == 0) {
     if (lane == 0) {
-      mbar_expect_tx(kv_full, 2 * ATT_TILE_BYTES);
-      tma_load_4d(sK, &p.tmK[ks], kv_full, 0, h, k_row0, b);
-      tma_load_4d(sV, &p.tmV[ks], kv_full, 0, h, k_row0, b);
-      for (int i = 0; i < nt; ++i) {
+      for (int i = 2; i < nt; ++i) {   // tiles 0 and 1 were issued in the prologue
         const int st = i & 1;
         const int qs = i < ntx ? 0 : 1;
         const int row0 = (qs == 0 ? i : i - ntx) * ATT_TILE;
@@ -119,48 +155,110 @@ attn_bwd_kernel(const __grid_constant__ AttnBwdParams p) {
     }
   } else if (warp == 1) {
     if (lane == 0) {
+      // Software pipeline: S^T/dP^T of tile i+1 are issued as soon as the compute warps have read
+      // tile i's, BEFORE the dV/dK/dQ MMAs of tile i, so exp/dS math of tile i+1 overlaps them.
       const uint32_t id_kn = make_idesc_bf16(128, 64, 0, 1);   // dV, dK
       const uint32_t id_nn = make_idesc_bf16(128, 64, 1, 1);   // dQ
-      const uint32_t k_addr = smem_u32(sK), v_addr = smem_u32(sV);
-      const uint32_t pt_addr = smem_u32(sPt), dst_addr = smem_u32(sdSt);
-      mbar_wait(kv_full, 0);
-      for (int i = 0; i < nt; ++i) {
+      constexpr uint64_t kStepK = 32 >> 4, kStepMN = 2048 >> 4, kTile = ATT_TILE_BYTES >> 4;
+      const uint64_t k_desc = desc_kmajor(smem_u32(sK), 0), v_desc = desc_kmajor(smem_u32(sV), 0);
+      const uint64_t k_desc_mn = desc_mnmajor(smem_u32(sK), 0, ATT_TILE_BYTES);
+      const uint64_t q_desc0 = desc_kmajor(smem_u32(sQ), 0), do_desc0 = desc_kmajor(smem_u32(sdO), 0);
+      const uint64_t q_desc0_mn = desc_mnmajor(smem_u32(sQ), 0, ATT_TILE_BYTES);
+      const uint64_t do_desc0_mn = desc_mnmajor(smem_u32(sdO), 0, ATT_TILE_BYTES);
+      const uint64_t pt_desc0 = desc_kmajor(smem_u32(sPt), 0), dst_desc0 = desc_kmajor(smem_u32(sdSt), 0);
+      const uint64_t dst_desc0_mn = desc_mnmajor(smem_u32(sdSt), 0, ATT_TILE_BYTES);
+      auto issue_s = [&](int i) {
         const int st = i & 1;
-        const uint32_t q_addr = smem_u32(sQ + st * ATT_TILE_BYTES);
-        const uint32_t do_addr = smem_u32(sdO + st * ATT_TILE_BYTES);
         const int qs = i < ntx ? 0 : 1;
         const int row0 = (qs == 0 ? i : i - ntx) * ATT_TILE;
         const int nq = (min(ATT_TILE, (qs == 0 ? p.N : p.M) - row0) + 15) & ~15;  // queries that exist
         const uint32_t id_kq = make_idesc_bf16(128, nq, 0, 0);
         mbar_wait(&qdo_full[st], (i >> 1) & 1);
         tc_fence_after();
+        TL(tls++, 10 + i);
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          umma_bf16(tm_St, desc_kmajor(k_addr, k), desc_kmajor(q_addr, k), id_kq, k > 0);
+          umma_bf16(tm_St, k_desc + k * kStepK, q_desc0 + st * kTile + k * kStepK, id_kq, k > 0);
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          umma_bf16(tm_dPt, desc_kmajor(v_addr, k), desc_kmajor(do_addr, k), id_kq, k > 0);
+          umma_bf16(tm_dPt, v_desc + k * kStepK, do_desc0 + st * kTile + k * kStepK, id_kq, k > 0);
         umma_commit(st_full);
+        TL(tls++, 20 + i);
+      };
+      mbar_wait(kv_full, 0);
+      issue_s(0);
+      for (int i = 0; i < nt; ++i) {
+        const int st = i & 1;
+        const int qs = i < ntx ? 0 : 1;
+        const int row0 = (qs == 0 ? i : i - ntx) * ATT_TILE;
+        const int nq = (min(ATT_TILE, (qs == 0 ? p.N : p.M) - row0) + 15) & ~15;
+        const uint64_t pt_desc = pt_desc0 + st * 2 * kTile, dst_desc = dst_desc0 + st * 2 * kTile;
         mbar_wait(pt_full, i & 1);
         tc_fence_after();
+        TL(tls++, 30 + i);
+        if (i + 1 < nt) issue_s(i + 1);
         for (int k = 0; k < nq / 16; ++k)
-          umma_bf16(tm_dV, desc_kmajor(pt_addr + (k >> 2) * ATT_TILE_BYTES, k & 3),
-                    desc_mnmajor(do_addr, k, ATT_TILE_BYTES), id_kn, (i > 0 || k > 0) ? 1u : 0u);
+          umma_bf16(tm_dV, pt_desc + (k >> 2) * kTile + (k & 3) * kStepK,
+                    do_desc0_mn + st * kTile + k * kStepMN, id_kn, (i > 0 || k > 0) ? 1u : 0u);
         for (int k = 0; k < nq / 16; ++k)
-          umma_bf16(tm_dK, desc_kmajor(dst_addr + (k >> 2) * ATT_TILE_BYTES, k & 3),
-                    desc_mnmajor(q_addr, k, ATT_TILE_BYTES), id_kn, (i > 0 || k > 0) ? 1u : 0u);
+          umma_bf16(tm_dK, dst_desc + (k >> 2) * kTile + (k & 3) * kStepK,
+                    q_desc0_mn + st * kTile + k * kStepMN, id_kn, (i > 0 || k > 0) ? 1u : 0u);
+        TL(tls++, 40 + i);
         if (i > 0) {
           mbar_wait(dq_empty, (i - 1) & 1);
           tc_fence_after();
         }
+        TL(tls++, 50 + i);
 #pragma unroll
         for (int k = 0; k < 8; ++k)
-          umma_bf16(tm_dQ, desc_mnmajor(dst_addr, k, ATT_TILE_BYTES),
-                    desc_mnmajor(k_addr, k, ATT_TILE_BYTES), id_nn, k > 0);
+          umma_bf16(tm_dQ, dst_desc0_mn + st * 2 * kTile + k * kStepMN, k_desc_mn + k * kStepMN, id_nn, k > 0);
         umma_commit(&qdo_empty[st]);
+        umma_commit(&buf_free[st]);
         umma_commit(dq_full);
+        TL(tls++, 60 + i);
       }
+      umma_commit(all_done);
     }
+  } else if (warp >= 10) {
+    // ------------------------------------------------------------ dQ drain warps
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;  // query row of the tile == TMEM lane
+    const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
+    for (int i = 0; i < nt; ++i) {
+      const int qs = i < ntx ? 0 : 1;
+      const int row0 = (qs == 0 ? i : i - ntx) * ATT_TILE;
+      const int q_valid = min(ATT_TILE, (qs == 0 ? p.N : p.M) - row0);
+      const int t0 = (qs == 0 ? 0 : p.N) + row0;
+      mbar_wait(dq_full, i & 1);
+      tc_fence_after();
+      uint32_t q0[32], q1[32];
+      tmem_ld32(tm_dQ + lane_off, q0);
+      tmem_ld32(tm_dQ + lane_off + 32, q1);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(dq_empty);       // TMEM tile is in registers: the MMA warp may overwrite it
+      // dq_full(i) also means every MMA that read P^T buffer (i & 1) has retired: reuse it as the
+      // staging tile (two 128-row x 128-byte halves, 128B swizzle) of an asynchronous TMA reduce-add.
+      uint8_t* stage = sPt + (i & 1) * 2 * ATT_TILE_BYTES;
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        *reinterpret_cast<uint4*>(stage + r * 128 + ((g ^ (r & 7)) << 4)) =
+            make_uint4(q0[4 * g], q0[4 * g + 1], q0[4 * g + 2], q0[4 * g + 3]);
+        *reinterpret_cast<uint4*>(stage + ATT_TILE_BYTES + r * 128 + ((g ^ (r & 7)) << 4)) =
+            make_uint4(q1[4 * g], q1[4 * g + 1], q1[4 * g + 2], q1[4 * g + 3]);
+      }
+      fence_proxy_async_smem();
+      named_bar_sync(2, 128);
+      if (warp == 10 && lane == 0) {
+        tma_reduce_add_3d(&p.tmdQ[qs], stage, h * ATT_HD, row0, b);
+        tma_reduce_add_3d(&p.tmdQ[qs], stage + ATT_TILE_BYTES, h * ATT_HD + 32, row0, b);
+        tma_commit_group();
+        tma_wait_group_read0();          // smem has been read: compute warps may refill the buffer
+        mbar_arrive(&stage_free[i & 1]);
+      }
+      (void)q_valid; (void)t0;
+    }
+    if (warp == 10 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   } else {
     // ---------------------------------------------------------------- compute
     const int cw = warp - 2;
@@ -172,6 +270,14 @@ attn_bwd_kernel(const __grid_constant__ AttnBwdParams p) {
     const bool k_ok = r < k_valid;
     const float sl2 = p.scale_log2;
     const long long lse_base = ((long long)b * p.H + h) * T;
+    float pre_lse = INFINITY, pre_del = 0.f;
+    if (ct < 128) {   // first query tile
+      const int qv0 = min(ATT_TILE, (ntx > 0 ? p.N : p.M));
+      if (ct < qv0) {
+        pre_lse = p.lse[lse_base + ct] * 1.4426950408889634f;
+        pre_del = p.delta[lse_base + ct];
+      }
+    }
     for (int i = 0; i < nt; ++i) {
       const int qs = i < ntx ? 0 : 1;
       const int row0 = (qs == 0 ? i : i - ntx) * ATT_TILE;
@@ -179,15 +285,28 @@ attn_bwd_kernel(const __grid_constant__ AttnBwdParams p) {
       const int t0 = (qs == 0 ? 0 : p.N) + row0;
       float* lse_s = sLse + (i & 1) * 128;
       float* del_s = sDelta + (i & 1) * 128;
-      if (ct < 128) {
-        const bool ok = ct < q_valid;
-        lse_s[ct] = ok ? p.lse[lse_base + t0 + ct] * 1.4426950408889634f : INFINITY;
-        del_s[ct] = ok ? p.delta[lse_base + t0 + ct] : 0.f;
+      if (ct < 128) {   // values were fetched from global one iteration ago
+        lse_s[ct] = pre_lse;
+        del_s[ct] = pre_del;
+      }
+      if (ct < 128 && i + 1 < nt) {   // prefetch for the next query tile; consumed after this tile's math
+        const int qs1 = i + 1 < ntx ? 0 : 1;
+        const int row1 = (qs1 == 0 ? i + 1 : i + 1 - ntx) * ATT_TILE;
+        const int qv1 = min(ATT_TILE, (qs1 == 0 ? p.N : p.M) - row1);
+        const int t1 = (qs1 == 0 ? 0 : p.N) + row1;
+        const bool ok = ct < qv1;
+        pre_lse = ok ? p.lse[lse_base + t1 + ct] * 1.4426950408889634f : INFINITY;
+        pre_del = ok ? p.delta[lse_base + t1 + ct] : 0.f;
       }
       named_bar_sync(1, 256);
+      TL(tls++, 70 + i);
       mbar_wait(st_full, i & 1);
       tc_fence_after();
-      if (i > 0) mbar_wait(dq_full, (i - 1) & 1);  // MMAs of tile i-1 no longer read sPt/sdSt
+      TL(tls++, 80 + i);
+      // P^T/dS^T buffer (i & 1): tile i-2's MMAs have retired and its dQ staging has been read out
+      mbar_wait(&stage_free[i & 1], ((i >> 1) & 1) ^ 1);
+      uint8_t* bufP = sPt + (i & 1) * 2 * ATT_TILE_BYTES;
+      uint8_t* bufD = sdSt + (i & 1) * 2 * ATT_TILE_BYTES;
       const int nq = (q_valid + 15) & ~15;
 #pragma unroll 1
       for (int c = 0; c < 2; ++c) {
@@ -196,18 +315,23 @@ attn_bwd_kernel(const __grid_constant__ AttnBwdParams p) {
         tmem_ld32(tm_St + lane_off + hf * 64 + c * 32, s);
         tmem_ld32(tm_dPt + lane_off + hf * 64 + c * 32, dp);
         tmem_ld_wait();
-        uint8_t* prow = sPt + hf * ATT_TILE_BYTES + r * 128;
-        uint8_t* drow = sdSt + hf * ATT_TILE_BYTES + r * 128;
+        uint8_t* prow = bufP + hf * ATT_TILE_BYTES + r * 128;
+        uint8_t* drow = bufD + hf * ATT_TILE_BYTES + r * 128;
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           float pe[8], de[8];
+          const int col0 = hf * 64 + c * 32 + g * 8;
+          const float4 l0 = *reinterpret_cast<const float4*>(lse_s + col0);
+          const float4 l1 = *reinterpret_cast<const float4*>(lse_s + col0 + 4);
+          const float4 e0 = *reinterpret_cast<const float4*>(del_s + col0);
+          const float4 e1 = *reinterpret_cast<const float4*>(del_s + col0 + 4);
+          const float lv[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
+          const float dv8[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const int col = hf * 64 + c * 32 + g * 8 + j;
-            const float pv =
-                k_ok ? ex2_approx(fmaf(__uint_as_float(s[g * 8 + j]), sl2, -lse_s[col])) : 0.f;
+            const float pv = k_ok ? ex2_approx(fmaf(__uint_as_float(s[g * 8 + j]), sl2, -lv[j])) : 0.f;
             pe[j] = pv;
-            de[j] = pv * (__uint_as_float(dp[g * 8 + j]) - del_s[col]) * p.scale;
+            de[j] = pv * (__uint_as_float(dp[g * 8 + j]) - dv8[j]) * p.scale;
           }
           uint4 u, w;
           u.x = pack_bf16x2(pe[0], pe[1]); u.y = pack_bf16x2(pe[2], pe[3]);
@@ -222,25 +346,10 @@ attn_bwd_kernel(const __grid_constant__ AttnBwdParams p) {
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(pt_full);
-      // drain dQ_i: thread = (query row r, 32-column chunk hf)
-      mbar_wait(dq_full, i & 1);
-      tc_fence_after();
-      {
-        uint32_t q[32];
-        tmem_ld32(tm_dQ + lane_off + hf * 32, q);
-        tmem_ld_wait();
-        tc_fence_before();
-        mbar_arrive(dq_empty);
-        if (r < q_valid) {
-          float* dst = p.dq_acc + ((long long)b * T + t0 + r) * (p.H * ATT_HD) + h * ATT_HD + hf * 32;
-#pragma unroll
-          for (int g = 0; g < 8; ++g)
-            red_add_v4(dst + g * 4, __uint_as_float(q[g * 4]), __uint_as_float(q[g * 4 + 1]),
-                       __uint_as_float(q[g * 4 + 2]), __uint_as_float(q[g * 4 + 3]));
-        }
-      }
+      TL(tls++, 90 + i);
     }
-    // dq_full(nt-1) was awaited above: all MMAs (incl. the last dV/dK updates) have retired.
+    mbar_wait(all_done, 0);   // every MMA (incl. the last dV/dK updates) has retired
+    tc_fence_after();
     {
       uint32_t a[32], c2[32];
       tmem_ld32(tm_dV + lane_off + hf * 32, a);
@@ -264,6 +373,7 @@ attn_bwd_kernel(const __grid_constant__ AttnBwdParams p) {
       }
     }
   }
+  TL(tls++, 200);
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem_base, 512);
@@ -322,6 +432,12 @@ attn_dq_convert_kernel(const float* __restrict__ acc, bf16* __restrict__ dq, int
 
 using namespace mmdit;
 
+extern "C" int mmdit_debug_attn_bwd_timeline(long long* buf, int block) {
+  cudaError_t e = cudaMemcpyToSymbol(g_bwd_timeline, &buf, sizeof(buf));
+  if (e == cudaSuccess) e = cudaMemcpyToSymbol(g_bwd_timeline_block, &block, sizeof(block));
+  return (int)e;
+}
+
 extern "C" int mmdit_attn_bwd(const mmdit_attn_args* a, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   MMDIT_REQUIRE(a, MMDIT_ERR_ARG, "attn_bwd: null args");
@@ -356,6 +472,14 @@ extern "C" int mmdit_attn_bwd(const mmdit_attn_args* a, void* stream_) {
     if (rc) return rc;
     rc = make_attn_tmap(&p.tmdO[s], a->d_o[s], a->ld_do[s], a->H, rows[s], a->B);
     if (rc) return rc;
+    {
+      uint64_t dims[3] = {(uint64_t)dmodel, (uint64_t)rows[s], (uint64_t)a->B};
+      uint64_t strides[2] = {(uint64_t)dmodel * 4, (uint64_t)T * dmodel * 4};
+      uint32_t box[3] = {32, ATT_TILE, 1};
+      rc = encode_tmap(&p.tmdQ[s], a->dq_acc + (s == 0 ? 0 : (size_t)a->N * dmodel), 3, dims, strides, box, 4,
+                       true);
+      if (rc) return rc;
+    }
     p.dk[s] = static_cast<bf16*>(a->dk[s]);
     p.dv[s] = static_cast<bf16*>(a->dv[s]);
     p.ld_dk[s] = a->ld_dk[s];

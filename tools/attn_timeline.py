@@ -32,3 +32,26 @@ for blk in [int(x) for x in (sys.argv[1:] or [1500, 1501, 1503])]:
     print(f"--- block {blk} (q tile {blk % 4}) : total {ev[-1][0] - t0} cycles")
     print(" ".join(f"{who}{eid}@{tt - t0}" for tt, who, eid in ev))
 L.mmdit_debug_attn_timeline(None, -1)
+
+# ---- backward
+o_x, o_c, lse = ops.attn_fwd(qs, ks, vs, B, H, N, M, 0.125, logit_bound=bound)
+do_x, do_c = torch.randn_like(o_x), torch.randn_like(o_c)
+dx, dc = torch.empty_like(qkv_x), torch.empty_like(qkv_c)
+dq, dk, dv = ((dx[:, i * d:(i + 1) * d], dc[:, i * d:(i + 1) * d]) for i in range(3))
+L.mmdit_debug_attn_bwd_timeline.argtypes = [C.c_void_p, C.c_int]
+for blk in [1500, 1503]:
+    buf.zero_()
+    assert L.mmdit_debug_attn_bwd_timeline(buf.data_ptr(), blk) == 0
+    ops.attn_bwd(qs, ks, vs, (o_x, o_c), lse, (do_x, do_c), dq, dk, dv, B, H, N, M, 0.125)
+    torch.cuda.synchronize()
+    t = buf.cpu().tolist()
+    ev = []
+    for base, who in ((0, "mma"), (256, "cmp")):
+        for i in range(128):
+            if base + 2 * i + 1 < len(t) and t[base + 2 * i]:
+                ev.append((t[base + 2 * i + 1], who, t[base + 2 * i]))
+    ev.sort()
+    t0 = ev[0][0]
+    print(f"--- BWD block {blk} (kv tile {blk % 4}) : total {ev[-1][0] - t0} cycles")
+    print(" ".join(f"{who}{eid}@{tt - t0}" for tt, who, eid in ev))
+L.mmdit_debug_attn_bwd_timeline(None, -1)

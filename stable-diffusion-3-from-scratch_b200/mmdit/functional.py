@@ -127,6 +127,35 @@ class LNModulateFn(Function):
         return dx.view(Bn, T, d), dmod[0], dmod[1]
 
 
+class LNModulateResFn(Function):
+    """adaLN modulate that also hands the residual stream through: returns (LN-mod(x), x).
+    Using the second output as the residual makes x a single-use tensor for autograd, so the sum
+    `d(LN path) + d(residual path)` happens inside the LN backward kernel (its `dres` operand)
+    instead of a separate elementwise add."""
+
+    @staticmethod
+    def forward(ctx, x, shift, scale):
+        Bn, T, d = x.shape
+        x2 = x.reshape(Bn * T, d)
+        y, mean, rstd = ops.ln_modulate_fwd(x2, shift, scale, T)
+        ctx.save_for_backward(x2, mean, rstd, scale)
+        ctx.shape = (Bn, T, d)
+        ctx.set_materialize_grads(False)
+        return y.view(Bn, T, d), x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, dy, dres):
+        x2, mean, rstd, scale = ctx.saved_tensors
+        Bn, T, d = ctx.shape
+        if dy is None:      # only the residual path was used
+            return dres, None, None
+        dmod = torch.empty((2, Bn, d), device=dy.device, dtype=BF16)
+        dr = None if dres is None else dres.reshape(Bn * T, d).contiguous()
+        dx = ops.ln_modulate_bwd(dy.reshape(Bn * T, d).contiguous(), x2, mean, rstd, scale, dr,
+                                 dmod[0], dmod[1], T)
+        return dx.view(Bn, T, d), dmod[0], dmod[1]
+
+
 class JointAttentionFn(Function):
     """QK-RMSNorm + 2-D RoPE (image tokens) + joint softmax attention over
     [image; text] (Attention.py:130-135,174-194,259-263,293,411-417).

@@ -7,7 +7,7 @@ normalise + modulate step is one fused 128-bit-vectorised kernel.
 import torch
 from torch import nn
 
-from mmdit.functional import LinearFn, LNModulateFn
+from mmdit.functional import LinearFn, LNModulateFn, LNModulateResFn
 from mmdit.shadow import packed_weight
 
 BF16 = torch.bfloat16
@@ -16,6 +16,11 @@ BF16 = torch.bfloat16
 def modulate(X, shift, scale):
     """LN(X) * (1 + scale[:, None]) + shift[:, None]; X [B,T,d], shift/scale [B,d] bf16 views."""
     return LNModulateFn.apply(X if X.dtype == BF16 else X.to(BF16), shift, scale)
+
+
+def modulate_keep(X, shift, scale):
+    """Like modulate, but also returns X for use as the residual (fuses the gradient sum)."""
+    return LNModulateResFn.apply(X if X.dtype == BF16 else X.to(BF16), shift, scale)
 
 
 class Norm(nn.Module):

@@ -17,7 +17,7 @@ from mmdit.functional import GatedLinearFn, LinearFn
 from mmdit.shadow import packed_weight
 from src.blocks.Attention import Attention
 from src.blocks.MLP import MLP, SwiGLU
-from src.blocks.Norm import Norm, modulate
+from src.blocks.Norm import Norm, modulate, modulate_keep
 
 BF16 = torch.bfloat16
 
@@ -95,14 +95,23 @@ class Transformer_Block_Dual(nn.Module):
         mod = LinearFn.apply(yp, packed_weight(self, "mod", ws), None, 0, len(ws), *ws)
         m = mod.unflatten(1, (len(ws), d)).unbind(1)
 
-        a_x, a_c = self.attn.attend(modulate(X, m[0], m[1]), modulate(c, m[2], m[3]), orig_shape)
+        # modulate_keep returns (LN-mod(X), X): taking the residual from the second output lets the LN
+        # backward kernel add the residual-path gradient itself (no separate elementwise add)
+        xn, X = modulate_keep(X, m[0], m[1])
+        if self.last:
+            cn = modulate(c, m[2], m[3])
+        else:
+            cn, c = modulate_keep(c, m[2], m[3])
+        a_x, a_c = self.attn.attend(xn, cn, orig_shape)
         X = self._gated(a_x, self.attn.out_proj_x, m[4], X, N)
         if not self.last:
             c = self._gated(a_c, self.attn.out_proj_c, m[8], c, M)
 
         mx = self._swiglu(self.MLP_x)
-        X = self._gated(mx.hidden(modulate(X, m[5], m[6])).reshape(B * N, -1), mx.w3, m[7], X, N)
+        xn, X = modulate_keep(X, m[5], m[6])
+        X = self._gated(mx.hidden(xn).reshape(B * N, -1), mx.w3, m[7], X, N)
         if not self.last:
             mc = self._swiglu(self.MLP_c)
-            c = self._gated(mc.hidden(modulate(c, m[9], m[10])).reshape(B * M, -1), mc.w3, m[11], c, M)
+            cn, c = modulate_keep(c, m[9], m[10])
+            c = self._gated(mc.hidden(cn).reshape(B * M, -1), mc.w3, m[11], c, M)
         return X, c

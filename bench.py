@@ -180,7 +180,7 @@ def run_product(args):
     import torch
     import torch.distributed as dist
     from mmdit import _lib
-    from mmdit.train import RFTrainer, host_batch
+    from mmdit.train import HostFeed, RFTrainer, host_batch
     from src.models.diff_model import diff_model
 
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -240,10 +240,15 @@ def run_product(args):
     value = world * BATCH * args.steps / (ms / 1e3)
 
     # ---- end-to-end arm: pinned host batch -> H2D every step, loss -> host every step
+    # (the H2D copy of batch i+1 is issued on a side stream while step i runs: mmdit.train.HostFeed)
     losses = []
+    feed = HostFeed(dev)
+    feed.submit(hbs[0])
 
     def e2e_step(i):
-        loss = trainer.step(trainer.to_device(hbs[i % nb]))
+        batch = feed.take()
+        feed.submit(hbs[(i + 1) % nb])      # next step's inputs start moving now
+        loss = trainer.step(batch)
         losses.append(float(loss))          # D2H read of the step's result (sync, like :472-473)
 
     for i in range(2):

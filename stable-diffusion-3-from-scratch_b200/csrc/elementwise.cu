@@ -222,11 +222,16 @@ swiglu_bwd_kernel(const bf16* __restrict__ da, const bf16* __restrict__ h12,
   float b1[8], b2[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) b1[j] = b2[j] = 0.f;
-  for (long long row = r0; row < r1; ++row) {
-    float g[8], x1[8], x2[8], d1[8], d2[8];
-    load8(da + row * hid + col, g);
-    load8(h12 + row * 2 * hid + col, x1);
-    load8(h12 + row * 2 * hid + hid + col, x2);
+  // 4 rows per trip: all 12 vector loads are issued before any math, so a warp keeps 6 KiB in
+  // flight (the grid alone does not fill the machine: ~20 warps per SM at cfg2 sizes)
+  auto body = [&](const uint4& ug, const uint4& u1, const uint4& u2, long long row) {
+    const float2 ga = unpack_bf16x2(ug.x), gb = unpack_bf16x2(ug.y), gc = unpack_bf16x2(ug.z), gd = unpack_bf16x2(ug.w);
+    const float2 xa = unpack_bf16x2(u1.x), xb = unpack_bf16x2(u1.y), xc = unpack_bf16x2(u1.z), xd = unpack_bf16x2(u1.w);
+    const float2 ya = unpack_bf16x2(u2.x), yb = unpack_bf16x2(u2.y), yc = unpack_bf16x2(u2.z), yd = unpack_bf16x2(u2.w);
+    const float g[8] = {ga.x, ga.y, gb.x, gb.y, gc.x, gc.y, gd.x, gd.y};
+    const float x1[8] = {xa.x, xa.y, xb.x, xb.y, xc.x, xc.y, xd.x, xd.y};
+    const float x2[8] = {ya.x, ya.y, yb.x, yb.y, yc.x, yc.y, yd.x, yd.y};
+    float d1[8], d2[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float sg = 1.f / (1.f + __expf(-x1[j]));
@@ -238,6 +243,24 @@ swiglu_bwd_kernel(const bf16* __restrict__ da, const bf16* __restrict__ h12,
     }
     store8(dh12 + row * 2 * hid + col, d1);
     store8(dh12 + row * 2 * hid + hid + col, d2);
+  };
+  long long row = r0;
+  for (; row + 3 < r1; row += 4) {
+    uint4 ug[4], u1[4], u2[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      ug[k] = *reinterpret_cast<const uint4*>(da + (row + k) * hid + col);
+      u1[k] = *reinterpret_cast<const uint4*>(h12 + (row + k) * 2 * hid + col);
+      u2[k] = *reinterpret_cast<const uint4*>(h12 + (row + k) * 2 * hid + hid + col);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) body(ug[k], u1[k], u2[k], row + k);
+  }
+  for (; row < r1; ++row) {
+    const uint4 ug = *reinterpret_cast<const uint4*>(da + row * hid + col);
+    const uint4 u1 = *reinterpret_cast<const uint4*>(h12 + row * 2 * hid + col);
+    const uint4 u2 = *reinterpret_cast<const uint4*>(h12 + row * 2 * hid + hid + col);
+    body(ug, u1, u2, row);
   }
   if (partial) {  // one fp32 row of column sums per row strip; folded by fold_rows_f32_kernel
     float* dst = partial + (long long)blockIdx.y * 2 * hid;
@@ -423,11 +446,21 @@ colsum_bf16_kernel(const bf16* __restrict__ in, float* __restrict__ out, long lo
 // out[n] += sum_rows in[row, n] (fp32 in), small row counts (per-batch partials).
 __global__ void fold_rows_f32_kernel(const float* __restrict__ in, float* __restrict__ out, int R,
                                      int n, long long ld) {
+  // grid.y row groups, each adds its partial column sum with one atomic (few groups -> cheap)
   const int col = blockIdx.x * blockDim.x + threadIdx.x;
   if (col >= n) return;
-  float acc = 0.f;
-  for (int r = 0; r < R; ++r) acc += in[r * ld + col];
-  out[col] += acc;
+  const int per = (R + gridDim.y - 1) / gridDim.y;
+  const int r0 = blockIdx.y * per, r1 = min(R, r0 + per);
+  float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+  int r = r0;
+  for (; r + 3 < r1; r += 4) {
+    acc0 += in[(long long)r * ld + col];
+    acc1 += in[(long long)(r + 1) * ld + col];
+    acc2 += in[(long long)(r + 2) * ld + col];
+    acc3 += in[(long long)(r + 3) * ld + col];
+  }
+  for (; r < r1; ++r) acc0 += in[(long long)r * ld + col];
+  if (r1 > r0) atomicAdd(out + col, (acc0 + acc1) + (acc2 + acc3));
 }
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ in, bf16* __restrict__ out,
                                      long long n) {
@@ -566,7 +599,7 @@ int mmdit_swiglu_bwd(const void* da, const void* h12, void* dh12, float* db12, f
                                                            (bf16*)dh12, db12 ? workspace : nullptr,
                                                            rows, hidden, rpb);
   if (db12)
-    fold_rows_f32_kernel<<<(2 * hidden + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+    fold_rows_f32_kernel<<<dim3((2 * hidden + 255) / 256, nrb >= 32 ? 16 : 1), 256, 0, (cudaStream_t)stream>>>(
         workspace, db12, nrb, 2 * hidden, 2 * (long long)hidden);
   return check_launch("swiglu_bwd_kernel", db12 ? 2 : 1);
 }
@@ -697,7 +730,7 @@ int mmdit_colsum_bf16(const void* in, float* out, int64_t rows, int32_t n, int64
 int mmdit_fold_rows_f32(const float* in, float* out, int32_t rows, int32_t n, int64_t ld,
                         void* stream) {
   MMDIT_REQUIRE(in && out && rows > 0 && n > 0, MMDIT_ERR_ARG, "fold_rows_f32: bad arguments");
-  fold_rows_f32_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(in, out, rows, n, ld);
+  fold_rows_f32_kernel<<<dim3((n + 255) / 256, rows >= 32 ? 16 : 1), 256, 0, (cudaStream_t)stream>>>(in, out, rows, n, ld);
   return check_launch("fold_rows_f32_kernel");
 }
 

@@ -140,7 +140,7 @@ ln_mod_fwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ shift,
 // g = dy*(1+s); dx = rstd*(g - mean(g) - xhat*mean(g*xhat)) (+ dres)
 // dshift[b] += sum_rows dy ; dscale[b] += sum_rows dy*xhat      (fp32 atomics)
 template <int NC>
-__global__ void __launch_bounds__(BWD_THREADS)
+__global__ void __launch_bounds__(BWD_THREADS, NC <= 3 ? 4 : 2)
 ln_mod_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
                   const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
                   const bf16* __restrict__ scale, const bf16* __restrict__ dres,
@@ -156,24 +156,7 @@ ln_mod_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
   if (r1 > (b + 1) * rows_per_batch) r1 = (b + 1) * rows_per_batch;
 
 
-  float one_plus[NC][8];
-  {
-    const bf16* sc = scale + b * ld_mod;
-#pragma unroll
-    for (int c = 0; c < NC; ++c) {
-      const int col = c * 256 + lane * 8;
-      if (col < d) {
-        float fc[8];
-        load8(sc + col, fc);
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          one_plus[c][j] = __bfloat162float(__float2bfloat16(1.f + fc[j]));
-      } else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) one_plus[c][j] = 0.f;
-      }
-    }
-  }
+  const bf16* sc = scale + b * ld_mod;
   float a_sh[NC][8], a_sc[NC][8];
 #pragma unroll
   for (int c = 0; c < NC; ++c)
@@ -182,21 +165,31 @@ ln_mod_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
 
   for (long long row = r0 + warp; row < r1; row += BWD_WARPS) {
     float g[NC][8], xh[NC][8];
+    uint4 rres[NC];   // residual-path gradient, fetched together with dy and x (one latency, not two)
     load_row<NC>(dy + row * d, d, lane, g);
     load_row<NC>(x + row * d, d, lane, xh);
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      const int col = c * 256 + lane * 8;
+      rres[c] = (dres && col < d) ? *reinterpret_cast<const uint4*>(dres + row * d + col)
+                                  : make_uint4(0u, 0u, 0u, 0u);
+    }
     const float mean = mean_in[row], rstd = rstd_in[row];
     float sg = 0.f, sgx = 0.f;
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
       const int col = c * 256 + lane * 8;
       if (col < d) {
+        float fc[8];
+        load8(sc + col, fc);   // L1-resident; recomputing 1+scale keeps 8*NC registers free
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
+          const float one_plus = __bfloat162float(__float2bfloat16(1.f + fc[j]));
           const float xhat = (xh[c][j] - mean) * rstd;
           const float dyv = g[c][j];
           a_sh[c][j] += dyv;
           a_sc[c][j] += dyv * xhat;
-          const float gv = dyv * one_plus[c][j];
+          const float gv = dyv * one_plus;
           xh[c][j] = xhat;
           g[c][j] = gv;
           sg += gv;
@@ -209,13 +202,9 @@ ln_mod_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
     for (int c = 0; c < NC; ++c) {
       const int col = c * 256 + lane * 8;
       if (col < d) {
-        float o[8];
-        if (dres) {
-          load8(dres + row * d + col, o);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) o[j] = 0.f;
-        }
+        const float2 r0v = unpack_bf16x2(rres[c].x), r1v = unpack_bf16x2(rres[c].y),
+                     r2v = unpack_bf16x2(rres[c].z), r3v = unpack_bf16x2(rres[c].w);
+        float o[8] = {r0v.x, r0v.y, r1v.x, r1v.y, r2v.x, r2v.y, r3v.x, r3v.y};
 #pragma unroll
         for (int j = 0; j < 8; ++j) o[j] += rstd * (g[c][j] - mg - xh[c][j] * mgx);
         store8(dx + row * d + col, o);
@@ -427,7 +416,7 @@ int mmdit_ln_modulate_fwd(const void* x, const void* shift, const void* scale, v
 
 int64_t mmdit_rowreduce_workspace_floats(int64_t rows, int32_t d, int64_t rows_per_batch) {
   if (rows <= 0 || d <= 0 || rows_per_batch <= 0) return 0;
-  const int64_t bpb = (rows_per_batch + 31) / 32;
+  const int64_t bpb = (rows_per_batch + 15) / 16;
   return (rows / rows_per_batch) * bpb * 2 * d;
 }
 
@@ -438,7 +427,7 @@ int mmdit_ln_modulate_bwd(const void* dy, const void* x, const float* mean, cons
   MMDIT_REQUIRE(dy && x && mean && rstd && scale && dx && dshift && dscale && workspace && rows > 0 &&
                     d % 8 == 0 && rows_per_batch > 0 && rows % rows_per_batch == 0,
                 MMDIT_ERR_ARG, "ln_modulate_bwd: bad arguments");
-  const int rpb = 32;
+  const int rpb = 16;
   const int bpb = (int)((rows_per_batch + rpb - 1) / rpb);
   const int nb = (int)(rows / rows_per_batch);
   const unsigned grid = (unsigned)(nb * bpb);
@@ -460,7 +449,7 @@ int mmdit_gate_bwd(const void* dout, const void* a, const void* gate, void* da, 
   MMDIT_REQUIRE(dout && a && gate && da && dgate && workspace && rows > 0 && d % 8 == 0 &&
                     rows_per_batch > 0 && rows % rows_per_batch == 0,
                 MMDIT_ERR_ARG, "gate_bwd: bad arguments");
-  const int rpb = 32;
+  const int rpb = 16;
   const int bpb = (int)((rows_per_batch + rpb - 1) / rpb);
   const int nb = (int)(rows / rows_per_batch);
   const unsigned grid = (unsigned)(nb * bpb);

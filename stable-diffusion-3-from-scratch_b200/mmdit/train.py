@@ -128,6 +128,31 @@ class GradBuckets:
             flat.mul_(1.0 / self.world_size)
 
 
+class HostFeed:
+    """Double-buffered host->device feed: the pinned batch of step i+1 is copied on a side stream
+    while step i computes (the reference blocks on three NCCL recvs per step, model_trainer.py:353-362)."""
+
+    def __init__(self, device):
+        self.device = device
+        self.stream = torch.cuda.Stream(device=device)
+        self.pending = None
+
+    def submit(self, host_batch_):
+        with torch.cuda.stream(self.stream):
+            dev = {k: v.to(self.device, non_blocking=True) for k, v in host_batch_.items()}
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+        self.pending = (dev, ev)
+
+    def take(self):
+        dev, ev = self.pending
+        torch.cuda.current_stream().wait_event(ev)
+        for v in dev.values():
+            v.record_stream(torch.cuda.current_stream())
+        self.pending = None
+        return dev
+
+
 class RFTrainer:
     def __init__(self, model, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01, clip=1.0,
                  world_size=1, process_group=None, use_graph=False, fused_optimizer=True):

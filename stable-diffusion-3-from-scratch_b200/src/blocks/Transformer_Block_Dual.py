@@ -83,14 +83,18 @@ class Transformer_Block_Dual(nn.Module):
                                 lin.weight, lin.bias)
         return o.view(B, T, d)
 
-    def forward(self, X, c, y, orig_shape):
+    def forward(self, X, c, y, orig_shape, yp=None):
+        """yp (optional): SiLU(y_proj(y)) computed by the caller for all blocks at once
+        (diff_model batches the per-block y projections into one GEMM); by default it is
+        computed here, as in the reference."""
         B, N, d = X.shape
         M = c.shape[1]
         X = X if X.dtype == BF16 else X.to(BF16)
         c = c if c.dtype == BF16 else c.to(BF16)
-        lin = self.y_proj[0]
-        yp = LinearFn.apply(y if y.dtype == BF16 else y.to(BF16), packed_weight(lin, "w", [lin.weight]),
-                            lin.bias.detach(), ops.EPI_SILU, 1, lin.weight, lin.bias)
+        if yp is None:
+            lin = self.y_proj[0]
+            yp = LinearFn.apply(y if y.dtype == BF16 else y.to(BF16), packed_weight(lin, "w", [lin.weight]),
+                                lin.bias.detach(), ops.EPI_SILU, 1, lin.weight, lin.bias)
         ws = self._mod_weights()
         mod = LinearFn.apply(yp, packed_weight(self, "mod", ws), None, 0, len(ws), *ws)
         m = mod.unflatten(1, (len(ws), d)).unbind(1)

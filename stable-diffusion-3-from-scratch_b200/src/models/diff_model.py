@@ -166,8 +166,15 @@ class diff_model(nn.Module):
         x = self.pos_enc(x_t if x_t.dtype in (BF16, F32) else x_t.float())
         x = self._linear(self.patch_emb, x)
 
-        for block in self.blocks:
-            x, cseq = block(x, cseq, y, orig_shape)
+        # y' = SiLU(y_proj_i(y)) of ALL blocks in one GEMM (they depend only on y), instead of one
+        # 64-row GEMM + SiLU + their backward chain per block (Transformer_Block_Dual.py:57)
+        yws = [blk.y_proj[0].weight for blk in self.blocks]
+        ybs = [blk.y_proj[0].bias for blk in self.blocks]
+        yp_all = LinearFn.apply(y, packed_weight(self, "y_proj_all", yws),
+                                torch.cat([b_.detach() for b_ in ybs]), ops.EPI_SILU, len(yws), *yws, *ybs)
+        yps = yp_all.unflatten(1, (len(yws), self.dim)).unbind(1)
+        for block, yp in zip(self.blocks, yps):
+            x, cseq = block(x, cseq, y, orig_shape, yp=yp)
 
         # output head (:339,342)
         x = self._linear(self.out_proj, self.out_norm(x, y))

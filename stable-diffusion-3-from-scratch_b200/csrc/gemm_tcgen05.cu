@@ -223,7 +223,13 @@ __device__ __forceinline__ void epilogue_fast(const GemmParams& p, const float* 
   }
 }
 
-template <int EV>
+// PAIR = true: launched as clusters of two CTAs (one TPC).  The pair owns a 256 x block_n output
+// tile: CTA `rank` holds A rows [rank*128, +128), the B rows [rank*block_n/2, +block_n/2) and the
+// accumulator rows [rank*128, +128) in its own TMEM; the leader issues tcgen05.mma.cta_group::2,
+// which reads both halves of B from both SMs.  Per SM and k-block that is 32 KB of operand
+// traffic (L2 -> smem) instead of 48 KB for the same FLOPs -- the single-CTA 128x256 tile is
+// L2-bandwidth bound at ~2/3 of the MMA rate on B200 (profiles/r01_gemm_shapes_*.log).
+template <int EV, bool PAIR>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -234,7 +240,11 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int block_n = p.block_n;
-  const int b_stage_bytes = block_n * BLOCK_K * 2;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;         // 0 = leader
+  const int unit0 = PAIR ? (blockIdx.x >> 1) : blockIdx.x;     // persistent work-unit stride
+  const int nunits = PAIR ? (gridDim.x >> 1) : gridDim.x;
+  const int b_rows = PAIR ? block_n / 2 : block_n;             // B rows staged by this CTA
+  const int b_stage_bytes = b_rows * BLOCK_K * 2;
   const int stage_bytes = A_STAGE_BYTES + b_stage_bytes;
   const int stages = p.stages;
 
@@ -259,16 +269,22 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
-      mbar_init(&tmem_empty[s], 4);  // one arrive per epilogue warp
+      mbar_init(&tmem_empty[s], PAIR ? 8 : 4);  // one arrive per epilogue warp (of both CTAs)
     }
     mbar_fence_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_slot, tmem_cols);
-    tmem_relinquish();
+    if constexpr (PAIR) {
+      tmem_alloc_pair(tmem_slot, tmem_cols);
+      tmem_relinquish_pair();
+    } else {
+      tmem_alloc(tmem_slot, tmem_cols);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();  // peer barriers initialised before any remote arrive / TMA
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -279,29 +295,35 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int work = blockIdx.x; work < total_work; work += gridDim.x) {
+      // In a pair both CTAs load their halves and credit the LEADER's full barrier, which
+      // expects the bytes of both (only the leader's MMA thread waits on it).
+      auto load = [&](void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1) {
+        if constexpr (PAIR) tma_load_2d_pair(dst, tm, mapa_u32(smem_u32(bar), 0), c0, c1);
+        else tma_load_2d(dst, tm, bar, c0, c1);
+      };
+      for (int work = unit0; work < total_work; work += nunits) {
         const int tile = work / p.split_k, ks = work % p.split_k;
-        const int m_blk = tile % p.tiles_m, n_blk = tile / p.tiles_m;
+        const int m_blk = PAIR ? (tile % p.tiles_m) * 2 + (int)rank : tile % p.tiles_m;  // 128-row units
+        const int n_blk = tile / p.tiles_m;
+        const int n0 = n_blk * block_n + (int)rank * (PAIR ? b_rows : 0);
         const int kb0 = ks * p.kb_per_split;
         const int kb1 = min(kb0 + p.kb_per_split, p.kb_total);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sA = smem + stage * stage_bytes;
           uint8_t* sB = sA + A_STAGE_BYTES;
-          mbar_expect_tx(&full_bar[stage], stage_bytes);
+          if (!PAIR || rank == 0) mbar_expect_tx(&full_bar[stage], PAIR ? 2 * stage_bytes : stage_bytes);
           if (!p.a_mn) {
-            tma_load_2d(sA, &p.tmA, &full_bar[stage], kb * BLOCK_K, m_blk * BLOCK_M);
+            load(sA, &p.tmA, &full_bar[stage], kb * BLOCK_K, m_blk * BLOCK_M);
           } else {
             for (int i = 0; i < BLOCK_M / 64; ++i)
-              tma_load_2d(sA + i * (BLOCK_K * 128), &p.tmA, &full_bar[stage],
-                          m_blk * BLOCK_M + i * 64, kb * BLOCK_K);
+              load(sA + i * (BLOCK_K * 128), &p.tmA, &full_bar[stage], m_blk * BLOCK_M + i * 64, kb * BLOCK_K);
           }
           if (!p.b_mn) {
-            tma_load_2d(sB, &p.tmB, &full_bar[stage], kb * BLOCK_K, n_blk * block_n);
+            load(sB, &p.tmB, &full_bar[stage], kb * BLOCK_K, n0);
           } else {
-            for (int i = 0; i < block_n / 64; ++i)
-              tma_load_2d(sB + i * (BLOCK_K * 128), &p.tmB, &full_bar[stage],
-                          n_blk * block_n + i * 64, kb * BLOCK_K);
+            for (int i = 0; i < b_rows / 64; ++i)
+              load(sB + i * (BLOCK_K * 128), &p.tmB, &full_bar[stage], n0 + i * 64, kb * BLOCK_K);
           }
           if (++stage == stages) { stage = 0; phase ^= 1; }
         }
@@ -309,13 +331,13 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
     }
   } else if (warp == 1) {
     // -------------------------------------------------------------- MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(BLOCK_M, block_n, p.a_mn, p.b_mn);
+    if (lane == 0 && rank == 0) {
+      const uint32_t idesc = make_idesc_bf16(PAIR ? 2 * BLOCK_M : BLOCK_M, block_n, p.a_mn, p.b_mn);
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
       uint32_t aphase = 0;
-      for (int work = blockIdx.x; work < total_work; work += gridDim.x) {
+      for (int work = unit0; work < total_work; work += nunits) {
         const int ks = work % p.split_k;
         const int kb0 = ks * p.kb_per_split;
         const int kb1 = min(kb0 + p.kb_per_split, p.kb_total);
@@ -333,12 +355,17 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
                 p.a_mn ? desc_mnmajor(a_addr, k, BLOCK_K * 128) : desc_kmajor(a_addr, k);
             const uint64_t bdesc =
                 p.b_mn ? desc_mnmajor(b_addr, k, BLOCK_K * 128) : desc_kmajor(b_addr, k);
-            umma_bf16(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            if constexpr (PAIR) umma_bf16_pair(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            else umma_bf16(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+          // frees the smem slot (in both CTAs of a pair) when these MMAs retire
+          if constexpr (PAIR) umma_commit_pair(&empty_bar[stage]);
+          else umma_commit(&empty_bar[stage]);
           if (++stage == stages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tmem_full[as]);  // accumulator ready for the epilogue
+        // accumulator ready for the epilogue warps (of both CTAs)
+        if constexpr (PAIR) umma_commit_pair(&tmem_full[as]);
+        else umma_commit(&tmem_full[as]);
         as ^= 1;
         if (as == 0) aphase ^= 1;
       }
@@ -348,9 +375,11 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
     const int ew = warp - 4;  // == warp % 4 -> TMEM lane quarter
     int as = 0;
     uint32_t aphase = 0;
-    for (int work = blockIdx.x; work < total_work; work += gridDim.x) {
+    const uint32_t leader_tmem_empty = PAIR ? mapa_u32(smem_u32(&tmem_empty[0]), 0) : 0u;
+    for (int work = unit0; work < total_work; work += nunits) {
       const int tile = work / p.split_k;
-      const int m_blk = tile % p.tiles_m, n_blk = tile / p.tiles_m;
+      const int m_blk = PAIR ? (tile % p.tiles_m) * 2 + (int)rank : tile % p.tiles_m;
+      const int n_blk = tile / p.tiles_m;
       const long long m0 = static_cast<long long>(m_blk) * BLOCK_M + ew * 32;
       [[maybe_unused]] GatePrefetch pf;
       if constexpr (EV == EV_GATE) gate_prefetch(p, lane, m0, n_blk * block_n + (lane & 7) * 8, pf);
@@ -376,7 +405,10 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
         if (c == nchunks - 1) {  // accumulator fully drained: hand the TMEM stage back early
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tmem_empty[as]);
+          if (lane == 0) {
+            if constexpr (PAIR) mbar_arrive_cluster(leader_tmem_empty + as * 8);
+            else mbar_arrive(&tmem_empty[as]);
+          }
         }
         float4* wrow = reinterpret_cast<float4*>(wbuf + lane * 64);
 #pragma unroll
@@ -421,7 +453,12 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem_base, tmem_cols);
+  if constexpr (PAIR) {
+    cluster_sync_all();  // no CTA exits (or frees TMEM) while its peer can still signal it
+    if (warp == 2) tmem_dealloc_pair(tmem_base, tmem_cols);
+  } else {
+    if (warp == 2) tmem_dealloc(tmem_base, tmem_cols);
+  }
 }
 
 static int pick_block_n(long long M, long long N, int sms) {
@@ -435,8 +472,46 @@ static int pick_block_n(long long M, long long N, int sms) {
     long long waves = (t + sms - 1) / sms;
     return (double)t / (double)(waves * sms) / cost;
   };
-  // 128-wide tiles run the MMA pipe at the same rate but double A traffic; small penalty
-  return eff(t256, 1.0) >= eff(t128, 1.08) ? 256 : 128;
+  // 128-wide tiles run as single CTAs (no cta_group::2) with twice the operand traffic per FLOP,
+  // which is L2-bandwidth bound on B200: they only pay off when 256-wide tiles leave most SMs idle
+  return eff(t256, 1.0) >= eff(t128, 1.35) ? 256 : 128;
+}
+
+template <int EV, bool PAIR>
+static int launch_variant(int grid, int smem_bytes, cudaStream_t stream, const GemmParams& p) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<EV, PAIR>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET);
+    if (e != cudaSuccess) {
+      set_last_error("gemm: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return (int)e;
+    }
+    attr_set = true;
+  }
+  if constexpr (PAIR) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<EV, true>, p);
+    if (e != cudaSuccess) {
+      set_last_error("gemm: cudaLaunchKernelEx (CTA pair): %s", cudaGetErrorString(e));
+      return (int)e;
+    }
+  } else {
+    gemm_tcgen05_kernel<EV, false><<<grid, GEMM_THREADS, smem_bytes, stream>>>(p);
+  }
+  return 0;
 }
 
 }  // namespace mmdit
@@ -469,10 +544,22 @@ extern "C" int mmdit_gemm_bf16(const mmdit_gemm_args* a, void* stream_) {
   p.M = (int)a->M; p.N = (int)a->N; p.K = (int)a->K;
   p.a_mn = a->a_major ? 1 : 0;
   p.b_mn = a->b_major ? 1 : 0;
-  p.block_n = a->force_block_n ? a->force_block_n : pick_block_n(a->M, a->N, sms);
+  // split-K GEMMs (explicit slices / fp32 accumulate) fill the machine through the split, not through
+  // narrower tiles: the split planners (here and ops._plan_split) assume 128x256 tiles
+  const bool will_split = a->split_k > 1 || (a->split_k <= 0 && a->accumulate && a->d_fp32 && a->K >= 8 * BLOCK_K);
+  p.block_n = a->force_block_n ? a->force_block_n
+              : (will_split && a->N > 128) ? 256 : pick_block_n(a->M, a->N, sms);
   MMDIT_REQUIRE(p.block_n == 64 || p.block_n == 128 || p.block_n == 256, MMDIT_ERR_ARG,
                 "gemm: block_n %d", p.block_n);
-  const int stage_bytes = A_STAGE_BYTES + p.block_n * BLOCK_K * 2;
+  // CTA pairs (cta_group::2) for every 256-wide tile with more than one 128-row block
+  static int env_pair = -1;
+  if (env_pair < 0) {
+    const char* e = getenv("MMDIT_GEMM_PAIR");
+    env_pair = e ? atoi(e) : 1;
+  }
+  const bool pair = env_pair && p.block_n == 256 && a->M > BLOCK_M && !(a->reserved & 16);
+  const int workers = pair ? sms / 2 : sms;  // persistent work units running concurrently
+  const int stage_bytes = A_STAGE_BYTES + (pair ? p.block_n / 2 : p.block_n) * BLOCK_K * 2;
   p.stages = (SMEM_BUDGET - 1024 - BAR_BYTES - EPI_STAGE_BYTES) / stage_bytes;
   if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
   {
@@ -483,7 +570,7 @@ extern "C" int mmdit_gemm_bf16(const mmdit_gemm_args* a, void* stream_) {
     }
     if (env_stages > 0 && p.stages > env_stages) p.stages = env_stages;
   }
-  p.tiles_m = (p.M + BLOCK_M - 1) / BLOCK_M;
+  p.tiles_m = pair ? (p.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M) : (p.M + BLOCK_M - 1) / BLOCK_M;
   p.tiles_n = (p.N + p.block_n - 1) / p.block_n;
   p.kb_total = (p.K + BLOCK_K - 1) / BLOCK_K;
   int split = a->split_k;
@@ -497,7 +584,7 @@ extern "C" int mmdit_gemm_bf16(const mmdit_gemm_args* a, void* stream_) {
       for (int s = 1; s <= max_split && s <= 64; ++s) {
         const int per = (p.kb_total + s - 1) / s;
         const long long units = (long long)tiles * ((p.kb_total + per - 1) / per);
-        const long long waves = (units + sms - 1) / sms;
+        const long long waves = (units + workers - 1) / workers;
         const double t = (double)waves * (per + 10.0);
         if (t < best - 1e-9) { best = t; split = s; }
       }
@@ -534,7 +621,7 @@ extern "C" int mmdit_gemm_bf16(const mmdit_gemm_args* a, void* stream_) {
     strides[0] = (uint64_t)a->lda * 2;
     int rc = encode_tmap(&p.tmA, a->A, 2, dims, strides, box, 2, true);
     if (rc) return rc;
-    if (!p.b_mn) { dims[0] = a->K; dims[1] = a->N; box[0] = BLOCK_K; box[1] = (uint32_t)p.block_n; }
+    if (!p.b_mn) { dims[0] = a->K; dims[1] = a->N; box[0] = BLOCK_K; box[1] = (uint32_t)(pair ? p.block_n / 2 : p.block_n); }
     else         { dims[0] = a->N; dims[1] = a->K; box[0] = 64;      box[1] = BLOCK_K; }
     strides[0] = (uint64_t)a->ldb * 2;
     rc = encode_tmap(&p.tmB, a->B, 2, dims, strides, box, 2, true);
@@ -543,7 +630,8 @@ extern "C" int mmdit_gemm_bf16(const mmdit_gemm_args* a, void* stream_) {
 
   const int smem_bytes = p.stages * stage_bytes + EPI_STAGE_BYTES + BAR_BYTES + 1024;
   const int total_work = tiles * p.split_k;
-  const int grid = total_work < sms ? total_work : sms;
+  const int grid = pair ? 2 * (total_work < workers ? total_work : workers)
+                        : (total_work < sms ? total_work : sms);
 
   // pick the epilogue variant: fast paths need whole 16-byte vectors everywhere
   auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
@@ -566,22 +654,14 @@ extern "C" int mmdit_gemm_bf16(const mmdit_gemm_args* a, void* stream_) {
       ev = EV_GATE;
     }
   }
-#define LAUNCH_EV(EVV)                                                                            \
-  case EVV: {                                                                                     \
-    static bool attr_set = false;                                                                 \
-    if (!attr_set) {                                                                              \
-      cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<EVV>,                              \
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET); \
-      if (e != cudaSuccess) {                                                                     \
-        set_last_error("gemm: cudaFuncSetAttribute: %s", cudaGetErrorString(e));                  \
-        return (int)e;                                                                            \
-      }                                                                                           \
-      attr_set = true;                                                                            \
-    }                                                                                             \
-    gemm_tcgen05_kernel<EVV><<<grid, GEMM_THREADS, smem_bytes, stream>>>(p);                      \
-  } break;
   MMDIT_REQUIRE(p.slice_stride == 0 || ev == EV_F32, MMDIT_ERR_ALIGN,
                 "gemm: split-K slices mode needs N %% 8 == 0 and 16-byte aligned D");
+  int rc = 0;
+#define LAUNCH_EV(EVV)                                                                 \
+  case EVV:                                                                            \
+    rc = pair ? launch_variant<EVV, true>(grid, smem_bytes, stream, p)                 \
+              : launch_variant<EVV, false>(grid, smem_bytes, stream, p);               \
+    break;
   switch (ev) {
     LAUNCH_EV(EV_GENERIC)
     LAUNCH_EV(EV_BF16)
@@ -591,5 +671,6 @@ extern "C" int mmdit_gemm_bf16(const mmdit_gemm_args* a, void* stream_) {
     LAUNCH_EV(EV_F32_ATOMIC)
   }
 #undef LAUNCH_EV
+  if (rc) return rc;
   return check_launch("gemm_tcgen05_kernel");
 }

@@ -61,11 +61,17 @@ def _rowmajor2d(t, name):
 
 
 # --------------------------------------------------------------------- GEMM
-def gemm(A, B, *, a_major=0, b_major=0, out=None, out_dtype=BF16, accumulate=False, split_k=0,
-         epilogue=EPI_NONE, bias=None, gate=None, rows_per_gate=0, resid=None, aux=None,
-         remap=None, out_rows=None, force_block_n=0, simt=False, _logical_m=None):
+def gemm(A, B, **kw):
     """D[M,N] = epilogue(A @ B^T).  A is stored [M,K] (a_major=0) or [K,M] (a_major=1);
-    B is stored [N,K] (b_major=0) or [K,N] (b_major=1)."""
+    B is stored [N,K] (b_major=0) or [K,N] (b_major=1).  Keyword arguments: see _gemm."""
+    return _gemm(A, B, **kw)
+
+
+def _gemm(A, B, *, a_major=0, b_major=0, out=None, out_dtype=BF16, accumulate=False, split_k=0,
+          epilogue=EPI_NONE, bias=None, gate=None, rows_per_gate=0, resid=None, aux=None,
+          remap=None, out_rows=None, force_block_n=0, simt=False, _logical_m=None):
+    """Body of gemm(); the split-K plans below recurse into _gemm so that a wrapper installed on
+    ops.gemm (bench.py's per-launch timers) sees every logical GEMM exactly once."""
     _need_cuda(A, B)
     _rowmajor2d(A, "A")
     _rowmajor2d(B, "B")
@@ -79,7 +85,7 @@ def gemm(A, B, *, a_major=0, b_major=0, out=None, out_dtype=BF16, accumulate=Fal
             and bias is None and aux is None and remap is None and not simt):
         # few output tiles, long reduction (adaLN dgrads with M = batch): split-K over all SMs
         # into an fp32 buffer, then one cast
-        acc = gemm(A, B, a_major=a_major, b_major=b_major, out_dtype=F32, accumulate=True)
+        acc = _gemm(A, B, a_major=a_major, b_major=b_major, out_dtype=F32, accumulate=True)
         return acc.to(BF16)
     if (out is None and out_dtype == F32 and not accumulate and remap is None and epilogue == EPI_NONE
             and bias is None and aux is None and not simt and N % 8 == 0 and split_k == 0):
@@ -88,8 +94,8 @@ def gemm(A, B, *, a_major=0, b_major=0, out=None, out_dtype=BF16, accumulate=Fal
         s = _plan_split(M, N, K)
         if s > 1:
             ws = torch.empty((s, M, N), device=A.device, dtype=F32)
-            gemm(A, B, a_major=a_major, b_major=b_major, out=ws.view(s * M, N), split_k=s,
-                 force_block_n=force_block_n, _logical_m=M)
+            _gemm(A, B, a_major=a_major, b_major=b_major, out=ws.view(s * M, N), split_k=s,
+                  force_block_n=force_block_n, _logical_m=M)
             out = torch.empty((M, N), device=A.device, dtype=F32)
             _lib.check(_lib.lib().mmdit_fold_slices_f32(_p(ws), _p(out), M * N, s, M * N, 0, _s()),
                        "mmdit_fold_slices_f32")

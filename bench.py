@@ -197,7 +197,11 @@ def run_product(args):
     if world > 1:  # DDP ctor semantics: every replica starts from rank 0's weights
         for p in model.parameters():
             dist.broadcast(p.data, 0)
-    trainer = RFTrainer(model, world_size=world, use_graph=not args.no_graph)
+    trainer = RFTrainer(model, world_size=world, use_graph=not args.no_graph,
+                        peer=None if args.exchange == "peer" else False)
+    exchange = ("none" if world == 1 else
+                "peer-memory kernel per bucket, overlapped with backward, inside the step graph"
+                if trainer.buckets.arena is not None else "NCCL all-reduce (torch.distributed)")
     C = CFG2["inCh"]
     nb = 4  # distinct host batches (3.3 MB each of text would be L2-resident; activations are not:
     #         one step touches > 20 GB of HBM, far beyond the 126 MB L2, so no explicit flush is needed)
@@ -311,7 +315,7 @@ def run_product(args):
         "config": {"workload": "MMDiT depth12/dim768/12 heads, 256px (32x32x16 latent, 256+154 tokens), "
                                "rectified-flow train step incl. clip+AdamW (BASELINE configs[1])",
                    "global_batch": world * BATCH, "batch_per_gpu": BATCH, "parallelism": f"dp{world}",
-                   "cuda_graph": bool(trainer.use_graph),
+                   "cuda_graph": bool(trainer.use_graph), "gradient_exchange": exchange,
                    "l2": "per-step working set (>20 GB) exceeds the 126 MB L2; no explicit flush"},
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "last_loss": losses[-1]},
@@ -333,6 +337,8 @@ def main():
     ap.add_argument("--impl", default="product", choices=["product", "reference"])
     ap.add_argument("--no-graph", action="store_true", help="do not capture the step into a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="data-parallel gradient exchange: our peer-memory kernel (default) or NCCL")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

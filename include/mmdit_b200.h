@@ -6,7 +6,8 @@
  * Each entry point below names the reference call site it replaces
  * (file:line under the reference root).  All pointers are DEVICE pointers
  * owned by the caller (PyTorch's allocator); the library never allocates,
- * frees or retains device memory, never synchronises the device, launches
+ * frees or retains device memory (one exception: the IPC-exportable gradient
+ * arena of mmdit_comm_alloc), never synchronises the device, launches
  * only on the stream passed in, and is CUDA-graph capturable.
  *
  * Conventions
@@ -239,6 +240,33 @@ int mmdit_adamw_step(const void* table, const void* chunks, int32_t n_chunks, fl
                      float lr, float beta1, float beta2, float eps, float weight_decay,
                      float max_norm, void* stream);
 int mmdit_adamw_chunk_elems(void);
+
+/* ------------------------------------------- data-parallel gradient exchange --
+ * Replaces the DDP reducer's bucketed NCCL all-reduce (model_trainer.py:224) with one kernel
+ * per bucket over NVLink peer memory: reduce-scatter + all-gather + mean in a single launch,
+ * CUDA-graph capturable, meant to run on a side stream while the backward continues.
+ * The gradient arena and the signal pad live in ONE allocation per rank made by
+ * mmdit_comm_alloc (cudaMalloc; the only device memory this library ever allocates -- it must be
+ * exportable through CUDA IPC, which PyTorch's sub-allocated blocks are not); peers map it with
+ * mmdit_comm_export / mmdit_comm_import (cudaIpc* handles, exchanged by the host over
+ * torch.distributed).  world in {1, 2, 4, 8}.  Summation order is rank 0..W-1 on every rank:
+ * results are bit-identical across ranks and across runs. */
+typedef struct mmdit_comm {
+  void* buf[8];    /* fp32 gradient arena of every rank (buf[rank] is the local one)        */
+  void* flag[8];   /* signal pad of every rank: uint32[16], zero-initialised                */
+  void* state;     /* local uint32[2] (epoch, finished-CTA counter), zero-initialised        */
+  int32_t world, rank;
+} mmdit_comm;
+int mmdit_comm_alloc(void** ptr, int64_t bytes);          /* cudaMalloc + zero */
+int mmdit_comm_free(void* ptr);
+int mmdit_comm_handle_bytes(void);                          /* sizeof(cudaIpcMemHandle_t) */
+int mmdit_comm_export(void* ptr, void* handle_out);
+int mmdit_comm_import(const void* handle, void** peer_ptr_out);
+int mmdit_comm_close(void* peer_ptr);
+/* arena[offset, offset+n) <- mean over ranks; offset, n in floats, multiples of 4.
+ * ctas <= 0: default grid.  Every rank must issue the same sequence of calls. */
+int mmdit_allreduce_mean_f32(const mmdit_comm* comm, int64_t offset, int64_t n, int32_t ctas,
+                             void* stream);
 
 #ifdef __cplusplus
 }

@@ -38,6 +38,13 @@ SIGNATURES = {
     "mmdit_fold_slices_f32": [vp, vp, i64, i32, i64, i32, vp],
     "mmdit_adamw_step": [vp, vp, i32, vp, f32, f32, f32, f32, f32, f32, vp],
     "mmdit_adamw_chunk_elems": [],
+    "mmdit_comm_alloc": [vp, i64],
+    "mmdit_comm_free": [vp],
+    "mmdit_comm_handle_bytes": [],
+    "mmdit_comm_export": [vp, vp],
+    "mmdit_comm_import": [vp, vp],
+    "mmdit_comm_close": [vp],
+    "mmdit_allreduce_mean_f32": [vp, i64, i64, i32, vp],
     "mmdit_rowreduce_workspace_floats": [i64, i32, i64],
     "mmdit_swiglu_bwd_workspace_floats": [i64, i32],
 }

@@ -20,6 +20,27 @@ from .ops import BF16, F32
 FUSED_GATE_EPILOGUE = os.environ.get("MMDIT_FUSED_GATE", "0") == "1"
 
 
+def _wgrad_slot(params):
+    """Data parallelism (mmdit.train.GradBuckets) gives every parameter a slot inside a flat fp32
+    gradient bucket.  When the parameters of one packed GEMM sit back to back in that bucket, the
+    wgrad GEMM writes the bucket directly: returns the fp32 [rows, K] matrix aliasing the slots
+    (None otherwise).  autograd then adopts the returned views as .grad -- no zero-fill of the
+    bucket, no accumulate pass, no copy."""
+    slots = [getattr(p, "_grad_slot", None) for p in params]
+    if not slots or any(s is None for s in slots):
+        return None
+    ptr = slots[0].data_ptr()
+    if ptr % 16:
+        return None
+    for s_ in slots:
+        if s_.data_ptr() != ptr:
+            return None
+        ptr += s_.numel() * 4
+    rows = sum(p.shape[0] for p in params)
+    K = params[0][0].numel()
+    return torch.as_strided(slots[0], (rows, K), (K, 1), slots[0].storage_offset())
+
+
 def _split_rows(t, sizes):
     """Row slices of a packed [sum(sizes), K] tensor (views, no copies)."""
     out, r = [], 0
@@ -44,6 +65,7 @@ class LinearFn(Function):
         ctx.save_for_backward(x2, wb, aux)
         ctx.meta = (x.shape, act, nw, [p.shape[0] for p in params[:nw]], len(params) > nw)
         ctx.wshapes = [p.shape for p in params[:nw]]
+        ctx.wparams = params[:nw]
         return y.reshape(*x.shape[:-1], wb.shape[0])
 
     @staticmethod
@@ -60,7 +82,7 @@ class LinearFn(Function):
         dx = None
         if ctx.needs_input_grad[0]:
             dx = ops.gemm(dy2, wb, b_major=1).reshape(xshape)
-        dw = ops.gemm(dy2, x2, a_major=1, b_major=1, out_dtype=F32)
+        dw = ops.gemm(dy2, x2, a_major=1, b_major=1, out_dtype=F32, out=_wgrad_slot(ctx.wparams))
         grads = [g.view(shp) for g, shp in zip(_split_rows(dw, sizes), ctx.wshapes)]
         if has_bias:
             grads += list(_split_rows(ops.colsum(dy2), sizes))
@@ -86,6 +108,7 @@ class GatedLinearFn(Function):
             aux = ops.gemm(a, wb, bias=bb)
             o = ops.gate_residual_fwd(aux, gate, resid, rows_per_batch)
         ctx.save_for_backward(a, wb, aux, gate)
+        ctx.wparam = w
         ctx.rpb = rows_per_batch
         ctx.has_bias = b is not None
         return o
@@ -100,7 +123,7 @@ class GatedLinearFn(Function):
         dab = torch.empty((Bn, n), device=do.device, dtype=F32) if ctx.has_bias else None
         da = ops.gate_bwd(do, aux, gate, dgate, dab, rpb)
         dx = ops.gemm(da, wb, b_major=1)
-        dw = ops.gemm(da, a, a_major=1, b_major=1, out_dtype=F32)
+        dw = ops.gemm(da, a, a_major=1, b_major=1, out_dtype=F32, out=_wgrad_slot([ctx.wparam])).view(ctx.wparam.shape)
         db = dab.sum(0) if ctx.has_bias else None
         return dx, None, None, dgate, do, None, dw, db
 
@@ -370,6 +393,7 @@ class SwiGLUHiddenFn(Function):
         h12 = ops.gemm(x2, wb, bias=None if b12 is None else b12.detach())
         a = ops.swiglu_fwd(h12)
         ctx.save_for_backward(x2, wb, h12)
+        ctx.wparam = w12
         ctx.meta = (x.shape, b12 is not None)
         return a.reshape(*x.shape[:-1], a.shape[-1])
 
@@ -380,7 +404,7 @@ class SwiGLUHiddenFn(Function):
         db = torch.zeros(h12.shape[1], device=da.device, dtype=F32) if has_bias else None
         dh = ops.swiglu_bwd(da.reshape(-1, da.shape[-1]).contiguous(), h12, db)
         dx = ops.gemm(dh, wb, b_major=1).reshape(xshape)
-        dw = ops.gemm(dh, x2, a_major=1, b_major=1, out_dtype=F32)
+        dw = ops.gemm(dh, x2, a_major=1, b_major=1, out_dtype=F32, out=_wgrad_slot([ctx.wparam]))
         return dx, None, dw, db
 
 

@@ -87,7 +87,12 @@ def _gemm(A, B, *, a_major=0, b_major=0, out=None, out_dtype=BF16, accumulate=Fa
         # into an fp32 buffer, then one cast
         acc = _gemm(A, B, a_major=a_major, b_major=b_major, out_dtype=F32, accumulate=True)
         return acc.to(BF16)
-    if (out is None and out_dtype == F32 and not accumulate and remap is None and epilogue == EPI_NONE
+    dst = None
+    if (out is not None and out.dtype == F32 and not accumulate and split_k == 0 and out.is_contiguous()
+            and tuple(out.shape) == (M, N)):
+        dst, out = out, None     # caller-provided destination (e.g. a gradient-bucket slot): still free to split
+    if (out is None and (out_dtype == F32 or dst is not None) and not accumulate and remap is None
+            and epilogue == EPI_NONE
             and bias is None and aux is None and not simt and N % 8 == 0 and split_k == 0):
         # wgrad-style outputs (few tiles, long reduction): split-K so that every SM has work; each
         # split writes its own fp32 slice (plain coalesced stores) and one small kernel folds them
@@ -96,10 +101,12 @@ def _gemm(A, B, *, a_major=0, b_major=0, out=None, out_dtype=BF16, accumulate=Fa
             ws = torch.empty((s, M, N), device=A.device, dtype=F32)
             _gemm(A, B, a_major=a_major, b_major=b_major, out=ws.view(s * M, N), split_k=s,
                   force_block_n=force_block_n, _logical_m=M)
-            out = torch.empty((M, N), device=A.device, dtype=F32)
+            out = dst if dst is not None else torch.empty((M, N), device=A.device, dtype=F32)
             _lib.check(_lib.lib().mmdit_fold_slices_f32(_p(ws), _p(out), M * N, s, M * N, 0, _s()),
                        "mmdit_fold_slices_f32")
             return out
+    if dst is not None:
+        out = dst
     if out is None:
         rows = out_rows if out_rows is not None else M
         if remap is not None and out_rows is None:

@@ -5,10 +5,13 @@
     loss = mean((v - (eps - x0))^2), backward, [gradient all-reduce], clip 1.0, AdamW, zero_grad
 
 One process per GPU.  Data parallelism (model_trainer.py:224) is a bucketed fp32 gradient
-all-reduce (mean) over NCCL; buckets follow the block structure and are launched on a side
-stream as soon as a block's gradients are final, so the reduction of block i overlaps the
-backward of block i-1.  With `use_graph=True` the whole single-GPU step (noise -> optimizer)
-is captured once into a CUDA graph and replayed.
+all-reduce (mean); buckets follow the block structure and are launched on a side stream as soon
+as a block's gradients are final, so the reduction of block i overlaps the backward of block
+i-1.  On CUDA the exchange is our own peer-memory kernel (mmdit/comm.py, csrc/comm.cu: one
+launch per bucket, reduce-scatter + all-gather + mean over NVLink), which is captured together
+with everything else: with `use_graph=True` the whole step (noise -> forward -> backward with
+the overlapped bucket reductions -> clip + AdamW) is ONE CUDA graph at any world size.
+torch.distributed collectives (NCCL / gloo) remain as the fallback exchange (`peer=False`).
 """
 import torch
 import torch.distributed as dist
@@ -45,9 +48,15 @@ class GradBuckets:
     param.grad tensors are views into the flat buffers, so the reduce needs no copies
     (torch DDP's default copies every gradient into its buckets: an extra 4*P-byte pass)."""
 
-    def __init__(self, named_params, world_size, process_group=None, device=None):
+    def __init__(self, named_params, world_size, process_group=None, device=None, peer=None, adjacent=()):
+        """adjacent: lists of parameters that one packed GEMM produces the gradients of (e.g. the
+        adaLN projections of a block); they are laid out back to back, in that order, so that the
+        wgrad GEMM can write the bucket directly (functional._wgrad_slot)."""
         self.world_size = world_size
         self.group = process_group
+        self.arena = None
+        self.overlap = False
+        self.main_stream = None
         groups = {}
         for name, p in named_params:
             if not p.requires_grad:
@@ -57,32 +66,74 @@ class GradBuckets:
             groups.setdefault(key, []).append(p)
         # backward reaches the LAST block first: reduce in that order
         self.order = sorted(groups, key=lambda k: (k[0] != "block", -k[1]))
+        first = {id(g[0]): g for g in adjacent if g}
+        member = {id(p) for g in adjacent for p in g}
+        for key, ps in groups.items():
+            laid = []
+            for p in ps:
+                if id(p) in first:
+                    laid.extend(first[id(p)])
+                elif id(p) not in member:
+                    laid.append(p)
+            if len(laid) == len(ps) and {id(p) for p in laid} == {id(p) for p in ps}:
+                groups[key] = laid
         self.buckets = []
-        for key in self.order:
+        self.ranges = []
+        dev = device or groups[self.order[0]][0].device
+        # every parameter's slot starts on a 64-byte boundary (vector loads/stores, TMA-free kernels)
+        sizes = [sum((p.numel() + 15) // 16 * 16 for p in groups[key]) for key in self.order]
+        padded = [(n + 63) // 64 * 64 for n in sizes]      # buckets start 256-byte aligned
+        if peer is None:
+            peer = (world_size in (2, 4, 8) and torch.device(dev).type == "cuda"
+                    and dist.is_available() and dist.is_initialized())
+        if peer:
+            from .comm import PeerArena
+            self.arena = PeerArena(sum(padded), dev, process_group)
+            self.side = torch.cuda.Stream(device=dev)
+        start = 0
+        for key, n, npad in zip(self.order, sizes, padded):
             ps = groups[key]
-            n = sum(p.numel() for p in ps)
-            flat = torch.zeros(n, device=device or ps[0].device, dtype=F32)
+            if self.arena is not None:
+                flat = self.arena.flat[start:start + n]
+            else:
+                flat = torch.zeros(n, device=dev, dtype=F32)
+            self.ranges.append((start, npad))
+            start += npad
             off = 0
             for p in ps:
-                p.grad = flat[off:off + p.numel()].view_as(p)
-                off += p.numel()
+                p._grad_slot = flat[off:off + p.numel()].view_as(p)
+                p.grad = None
+                off += (p.numel() + 15) // 16 * 16
             self.buckets.append((key, flat, ps))
+        self._seen = set()
 
     def zero(self):
+        if self.arena is not None:
+            self.arena.flat.zero_()
+            return
         for _, flat, _ in self.buckets:
             flat.zero_()
 
-    def rebind(self):
-        """Make sure .grad still points into the buckets (autograd accumulates in place)."""
-        for _, flat, ps in self.buckets:
-            off = 0
+    def reset(self):
+        """Start of a step: drop every .grad.  The backward then either writes a parameter's bucket
+        slot directly (packed wgrad GEMMs) or autograd hands over a fresh tensor that the hook
+        copies into the slot -- the buckets are never zero-filled or accumulated into."""
+        for _, _, ps in self.buckets:
             for p in ps:
-                view = flat[off:off + p.numel()].view_as(p)
-                if p.grad is None or p.grad.data_ptr() != view.data_ptr():
-                    if p.grad is not None:
-                        view.copy_(p.grad)
-                    p.grad = view
-                off += p.numel()
+                p.grad = None
+        self.begin_step()
+
+    def _adopt(self, p):
+        """.grad of `p` is final: make it live in its bucket slot."""
+        slot = p._grad_slot
+        if p.grad is None:
+            slot.zero_()
+        elif p.grad.data_ptr() != slot.data_ptr():
+            slot.copy_(p.grad)
+            self.copied_elems += p.numel()
+        else:
+            self.direct_elems += p.numel()
+        p.grad = slot
 
     # ---- overlap: launch a bucket's all-reduce the moment its last gradient has landed
     def install_hooks(self):
@@ -91,24 +142,58 @@ class GradBuckets:
         self._works = [None] * len(self.buckets)
         for bi, (_, _, ps) in enumerate(self.buckets):
             for p in ps:
-                p.register_post_accumulate_grad_hook(lambda _p, bi=bi: self._ready(bi))
+                p.register_post_accumulate_grad_hook(lambda _p, bi=bi: self._ready(bi, _p))
 
     def begin_step(self):
         self._count = [0] * len(self.buckets)
         self._works = [None] * len(self.buckets)
+        self._seen = set()
+        self.direct_elems = self.copied_elems = 0     # gradients written in place / copied into their slot
+        if self.arena is not None:
+            # the stream the backward runs on (inside a capture: the capturing stream); the hooks
+            # fire on autograd's thread, so it is pinned here rather than looked up there
+            self.main_stream = torch.cuda.current_stream()
 
     def _launch(self, bi):
+        if self.arena is not None:
+            # fork: the side stream picks up after everything issued so far (this bucket's
+            # gradients), then runs the bucket's exchange kernel next to the rest of the backward
+            main = self.main_stream or torch.cuda.current_stream()
+            ev = torch.cuda.Event()
+            ev.record(main)
+            self.side.wait_event(ev)
+            off, n = self.ranges[bi]
+            self.arena.all_reduce_mean(off, n, stream=self.side)
+            self._works[bi] = True
+            return
         flat = self.buckets[bi][1]
         self._works[bi] = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
 
-    def _ready(self, bi):
+    def _ready(self, bi, p):
+        with torch.no_grad():
+            self._adopt(p)
+        self._seen.add(id(p))
         self._count[bi] += 1
         if self.overlap and self.world_size > 1 and self._count[bi] == len(self.buckets[bi][2]):
             self._launch(bi)
 
+    def _adopt_missing(self):
+        """Parameters no gradient reached this step (or every one, when no hooks are installed)."""
+        with torch.no_grad():
+            for _, _, ps in self.buckets:
+                for p in ps:
+                    if id(p) not in self._seen:
+                        self._adopt(p)
+                        self._seen.add(id(p))
+
     def all_reduce_mean(self):
         """Non-overlapped variant: reduce every bucket now (async launches, then wait + mean)."""
+        self._adopt_missing()
         if self.world_size == 1:
+            return
+        if self.arena is not None:
+            for off, n in self.ranges:
+                self.arena.all_reduce_mean(off, n)
             return
         works = [dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
                  for _, flat, _ in self.buckets]
@@ -118,11 +203,18 @@ class GradBuckets:
 
     def finish(self):
         """Wait for every bucket (launching the ones no hook fired for) and apply DDP's mean."""
+        self._adopt_missing()
         if self.world_size == 1:
             return
         for bi in range(len(self.buckets)):
             if self._works[bi] is None:
                 self._launch(bi)
+        if self.arena is not None:
+            # join: the optimizer (current stream) runs after the last exchange kernel
+            ev = torch.cuda.Event()
+            ev.record(self.side)
+            torch.cuda.current_stream().wait_event(ev)
+            return
         for bi, (_, flat, _) in enumerate(self.buckets):
             self._works[bi].wait()
             flat.mul_(1.0 / self.world_size)
@@ -155,15 +247,16 @@ class HostFeed:
 
 class RFTrainer:
     def __init__(self, model, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01, clip=1.0,
-                 world_size=1, process_group=None, use_graph=False, fused_optimizer=True):
+                 world_size=1, process_group=None, use_graph=False, fused_optimizer=True, peer=None):
         self.model = model
         self.device = next(model.parameters()).device
         self.clip = clip
         self.world_size = world_size
         self.use_graph = use_graph
         self.params = [p for p in model.parameters() if p.requires_grad]
+        adjacent = [m._mod_weights() for m in model.modules() if hasattr(m, "_mod_weights")]
         self.buckets = GradBuckets(list(model.named_parameters()), world_size, process_group,
-                                   self.device) if world_size > 1 else None
+                                   self.device, peer=peer, adjacent=adjacent) if world_size > 1 else None
         if self.buckets is not None:
             self.buckets.install_hooks()
         self.fused_optimizer = fused_optimizer
@@ -211,9 +304,7 @@ class RFTrainer:
 
     def _zero(self):
         if self.buckets is not None:
-            self.buckets.rebind()
-            self.buckets.zero()
-            self.buckets.begin_step()
+            self.buckets.reset()
         else:
             self.opt.zero_grad(set_to_none=True)                      # :503
 
@@ -256,10 +347,19 @@ class RFTrainer:
                 self.loss = self._fwd_bwd(self.static)
                 self._update()
             return
+        if self.buckets.arena is not None:
+            # peer-memory exchange: plain kernels on a forked side stream, so the overlapped
+            # bucket reductions are captured with the rest of the step into one graph
+            with torch.cuda.graph(self.graph):
+                self.buckets.reset()
+                self.loss = self._fwd_bwd(self.static)
+                self._update()
+            return
         self.buckets.overlap = False            # hooks stay silent while capturing / replaying
         with torch.cuda.graph(self.graph):
-            self.buckets.zero()                  # buckets persist across replays: clear inside the graph
+            self.buckets.reset()
             self.loss = self._fwd_bwd(self.static)
+            self.buckets._adopt_missing()
         self.buckets.all_reduce_mean()
         self.graph_opt = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph_opt):

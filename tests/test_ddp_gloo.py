@@ -20,6 +20,7 @@ class Toy(nn.Module):
         self.blocks = nn.ModuleList([nn.Linear(8, 8) for _ in range(3)])
         self.head = nn.Linear(8, 4)
         self.frozen = nn.Parameter(torch.ones(3), requires_grad=False)
+        self.unused = nn.Parameter(torch.ones(5))      # never reached by backward: slot must read 0
 
     def forward(self, x):
         for b in self.blocks:
@@ -44,15 +45,17 @@ def _worker(rank, world, port, q):
     y = torch.randn(2 * world, 4, generator=g)
     sl = slice(2 * rank, 2 * rank + 2)
     for _ in range(2):                      # two steps: buckets must be reusable
-        buckets.rebind(); buckets.zero(); buckets.begin_step()
+        buckets.reset()       # .grad dropped; the hooks move each fresh gradient into its bucket slot
         ((model(x[sl]) - y[sl]) ** 2).mean().backward()
         buckets.finish()
     grads = {k: p.grad.clone() for k, p in model.named_parameters() if p.requires_grad}
+    assert float(model.unused.grad.abs().max()) == 0.0
     # single-process reference on the full batch
     ref = Toy()
     ref.load_state_dict(model.state_dict())
     ((ref(x) - y) ** 2).mean().backward()
-    err = max(float((grads[k] - p.grad).abs().max()) for k, p in ref.named_parameters() if p.requires_grad)
+    err = max(float((grads[k] - p.grad).abs().max()) for k, p in ref.named_parameters()
+              if p.requires_grad and p.grad is not None)
     views_ok = all(p.grad.data_ptr() >= flat.data_ptr() and p.grad.data_ptr() < flat.data_ptr() + flat.numel() * 4
                    for _, flat, ps in buckets.buckets for p in ps)
     q.put((rank, err, order, [k for k, _, _ in buckets.buckets], views_ok))

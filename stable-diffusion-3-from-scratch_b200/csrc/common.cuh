@@ -130,6 +130,17 @@ __device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* m, const vo
       "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+// TMA store of a (swizzled) smem tile into a global tensor; bulk-group completion.  Elements of
+// the box that fall outside the tensor are not written (ragged M / N edges need no masking).
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(m),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_wait_group_read1() {
+  asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+}
+__device__ __forceinline__ void tma_wait_group0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_wait_group_read0() {
   asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");

@@ -32,6 +32,7 @@ constexpr int EPI_STAGE_BYTES = 4 * 32 * 64 * 4;  // 4 warps x (32 rows x 64 fp3
 
 struct GemmParams {
   CUtensorMap tmA, tmB;
+  CUtensorMap tmD;  // bf16 output as {N, M}, box {64, 32}, 128B swizzle (TMA-store epilogues)
   int M, N, K;
   int block_n, stages;
   int a_mn, b_mn;
@@ -135,7 +136,13 @@ __device__ __forceinline__ void epilogue8(const GemmParams& p, long long m, long
 // Epilogue variants.  The fast ones are straight-line code for the hot GEMMs of the block
 // (all run-time flags resolved at compile time, full 8-column vectors, 16-byte aligned rows);
 // EV_GENERIC keeps every option behind run-time flags (tails, remap, SiLU, odd alignments).
-enum { EV_GENERIC = 0, EV_BF16 = 1, EV_BF16_BIAS = 2, EV_GATE = 3, EV_F32 = 4, EV_F32_ATOMIC = 5 };
+enum { EV_GENERIC = 0, EV_BF16 = 1, EV_BF16_BIAS = 2, EV_GATE = 3, EV_F32 = 4, EV_F32_ATOMIC = 5,
+       EV_BF16_TMA = 6 };
+// EV_BF16_TMA (bf16 output, optional fp32 bias): each epilogue thread owns one accumulator row
+// (its TMEM lane); a 64-column chunk is converted in registers, written as one 128-byte row of
+// a 128B-swizzled [32 x 64] bf16 staging tile (conflict-free 16-byte stores), and the tile leaves
+// through one TMA store.  No shared-memory read-back, no per-thread global stores, ragged M / N
+// edges clipped by the TMA unit; two staging tiles per warp keep a store in flight.
 
 // Operands of the gated-residual epilogue for one 64-column chunk: 8 passes x (gate, resid),
 // loaded as a batch (and before the accumulator is needed) so their latency is paid once.
@@ -376,6 +383,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
     int as = 0;
     uint32_t aphase = 0;
     const uint32_t leader_tmem_empty = PAIR ? mapa_u32(smem_u32(&tmem_empty[0]), 0) : 0u;
+    [[maybe_unused]] int tma_buf = 0;
     for (int work = unit0; work < total_work; work += nunits) {
       const int tile = work / p.split_k;
       const int m_blk = PAIR ? (tile % p.tiles_m) * 2 + (int)rank : tile % p.tiles_m;
@@ -392,6 +400,57 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
       float* wbuf = reinterpret_cast<float*>(stage_buf + ew * (32 * 64 * 4));
       const int nchunks = block_n / 64;
       const int sub_row = lane >> 3, seg = lane & 7;
+      if constexpr (EV == EV_BF16_TMA) {
+        uint8_t* sbase = stage_buf + ew * (32 * 64 * 4);   // two 4 KiB bf16 tiles (1024 B aligned)
+        for (int c = 0; c < nchunks; ++c) {
+          const int n = n_blk * block_n + c * 64;
+          uint32_t r0[32], r1[32];
+          tmem_ld32(taddr + c * 64, r0);
+          tmem_ld32(taddr + c * 64 + 32, r1);
+          tmem_ld_wait();
+          if (c == nchunks - 1) {  // accumulator drained: hand the TMEM stage back
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              if constexpr (PAIR) mbar_arrive_cluster(leader_tmem_empty + as * 8);
+              else mbar_arrive(&tmem_empty[as]);
+            }
+          }
+          if (n >= p.N || m0 >= p.M) continue;  // whole chunk beyond a ragged edge
+          uint8_t* tile = sbase + (tma_buf & 1) * 4096;
+          // the store that last used this tile (two chunks ago) must have finished reading it
+          if (lane == 0) tma_wait_group_read1();
+          __syncwarp();
+          uint8_t* prow = tile + lane * 128;
+          const float* bp = reinterpret_cast<const float*>(p.bias);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint32_t* src = j < 4 ? &r0[8 * j] : &r1[8 * (j - 4)];
+            float v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(src[i]);
+            if (bp) {   // N % 8 == 0 and n + 8j < N is checked per 8-column group
+              if (n + 8 * j < p.N) {
+                const float4 b0 = __ldg(reinterpret_cast<const float4*>(bp + n + 8 * j));
+                const float4 b1 = __ldg(reinterpret_cast<const float4*>(bp + n + 8 * j + 4));
+                v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+                v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+              }
+            }
+            uint4 u;
+            u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]);
+            u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
+            *reinterpret_cast<uint4*>(prow + ((j ^ (lane & 7)) << 4)) = u;
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0 && !(p.debug & 1)) {
+            tma_store_2d(&p.tmD, tile, n, static_cast<int>(m0));
+            tma_commit_group();
+          }
+          ++tma_buf;
+        }
+      } else
       for (int c = 0; c < nchunks; ++c) {
         if constexpr (EV == EV_GATE) {
           if (c > 0) gate_prefetch(p, lane, m0, n_blk * block_n + c * 64 + seg * 8, pf);
@@ -448,6 +507,9 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
       }
       as ^= 1;
       if (as == 0) aphase ^= 1;
+    }
+    if constexpr (EV == EV_BF16_TMA) {
+      if (lane == 0) tma_wait_group0();  // staging tiles must outlive their stores
     }
   }
 
@@ -646,7 +708,13 @@ extern "C" int mmdit_gemm_bf16(const mmdit_gemm_args* a, void* stream_) {
         else if (p.split_k > 1 || a->accumulate) ev = EV_F32_ATOMIC;  // red.add is also a valid "+="
       }
     } else if (a->epilogue == MMDIT_EPI_NONE && !a->aux) {
-      if (!a->bias) ev = EV_BF16;
+      static int env_tma = -1;
+      if (env_tma < 0) {
+        const char* e = getenv("MMDIT_GEMM_TMA_STORE");
+        env_tma = e ? atoi(e) : 1;
+      }
+      if (env_tma && bias_ok && a->N >= 64) ev = EV_BF16_TMA;
+      else if (!a->bias) ev = EV_BF16;
       else if (bias_ok) ev = EV_BF16_BIAS;
     } else if (a->epilogue == MMDIT_EPI_GATE_RESID && a->aux && bias_ok && al16(a->aux) &&
                al16(a->gate) && al16(a->resid) && a->ld_aux % 8 == 0 && a->ld_gate % 8 == 0 &&
@@ -656,6 +724,12 @@ extern "C" int mmdit_gemm_bf16(const mmdit_gemm_args* a, void* stream_) {
   }
   MMDIT_REQUIRE(p.slice_stride == 0 || ev == EV_F32, MMDIT_ERR_ALIGN,
                 "gemm: split-K slices mode needs N %% 8 == 0 and 16-byte aligned D");
+  if (ev == EV_BF16_TMA) {
+    uint64_t dims[2] = {(uint64_t)a->N, (uint64_t)a->M}, strides[1] = {(uint64_t)a->ldd * 2};
+    uint32_t box[2] = {64, 32};
+    int rc_d = encode_tmap(&p.tmD, a->D, 2, dims, strides, box, 2, true);
+    if (rc_d) return rc_d;
+  }
   int rc = 0;
 #define LAUNCH_EV(EVV)                                                                 \
   case EVV:                                                                            \
@@ -669,6 +743,7 @@ extern "C" int mmdit_gemm_bf16(const mmdit_gemm_args* a, void* stream_) {
     LAUNCH_EV(EV_GATE)
     LAUNCH_EV(EV_F32)
     LAUNCH_EV(EV_F32_ATOMIC)
+    LAUNCH_EV(EV_BF16_TMA)
   }
 #undef LAUNCH_EV
   if (rc) return rc;

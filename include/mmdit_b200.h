@@ -54,7 +54,8 @@ enum {
   MMDIT_EPI_GATE_RESID = 1,/* D = (acc+bias) * gate[m/rows_per_gate, n] + resid */
   MMDIT_EPI_SILU = 2,      /* D = silu(acc+bias)                                */
   MMDIT_EPI_RESID = 3,     /* D = acc + bias + resid                            */
-  MMDIT_EPI_SWIGLU = 4     /* B rows interleaved per 64: [gate|up]; D[M,N/2] = silu(g)*u; aux = raw acc+bias */
+  MMDIT_EPI_SWIGLU = 4     /* B = [gate rows; up rows] (xformers w12, MLP.py:19): D[M,N/2] = silu(g)*u,
+                              aux[M,N] = acc+bias (bf16, required); needs N % 256 == 0, M > 128 */
 };
 
 typedef struct mmdit_gemm_args {

@@ -311,6 +311,19 @@ attn_bwd_kernel(const __grid_constant__ AttnBwdParams p) {
 #pragma unroll 1
       for (int c = 0; c < 2; ++c) {
         if (hf * 64 + c * 32 >= nq) break;  // warp-uniform: these query columns do not exist
+        if (quarter * 32 >= k_valid) {
+          // partial key tile: no key row of this warp exists -> P^T = dS^T = 0, no exp / TMEM traffic
+          // (dS^T must be exact zeros: dQ sums over the key rows)
+          uint8_t* prow = bufP + hf * ATT_TILE_BYTES + r * 128;
+          uint8_t* drow = bufD + hf * ATT_TILE_BYTES + r * 128;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int off = ((c * 4 + g) ^ (r & 7)) << 4;
+            *reinterpret_cast<uint4*>(prow + off) = make_uint4(0u, 0u, 0u, 0u);
+            *reinterpret_cast<uint4*>(drow + off) = make_uint4(0u, 0u, 0u, 0u);
+          }
+          continue;
+        }
         uint32_t s[32], dp[32];
         tmem_ld32(tm_St + lane_off + hf * 64 + c * 32, s);
         tmem_ld32(tm_dPt + lane_off + hf * 64 + c * 32, dp);

@@ -186,6 +186,11 @@ attn_fwd_kernel(const __grid_constant__ AttnFwdParams p) {
     const bool use_bound = bound >= 0.f && bound <= 24.f;
     const float bound_l2 = bound * 1.4426950408889634f;
     if (use_bound) m = bound / p.scale;   // so that lse = m*scale + log(l) below stays valid
+    // A partial query tile (e.g. the 26 text rows left after a full 128-row tile) leaves whole warps
+    // without a valid row: they keep the barrier protocol going but skip the softmax math (their P
+    // rows stay whatever the buffer held -- every output row depends on its own P row only, and
+    // those rows are never stored).
+    const bool warp_active = quarter * 32 < q_valid;
     for (int j = 0; j < nkv; ++j) {
       const int ks = j < ntx ? 0 : 1;
       const int row0 = (ks == 0 ? j : j - ntx) * ATT_TILE;
@@ -196,6 +201,11 @@ attn_fwd_kernel(const __grid_constant__ AttnFwdParams p) {
       mbar_wait(s_full, j & 1);
       tc_fence_after();
       TL(tls++, 60 + j);
+      if (!warp_active) {
+        tc_fence_before();
+        mbar_arrive(p_full);
+        continue;
+      }
       float alpha = 1.f, mb, m_new = m;
       if (!use_bound) {
         // pass 1: row maximum (4 independent chains; TMEM loads issued in pairs)

@@ -234,7 +234,7 @@ swiglu_bwd_kernel(const bf16* __restrict__ da, const bf16* __restrict__ h12,
     float d1[8], d2[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const float sg = 1.f / (1.f + __expf(-x1[j]));
+      const float sg = __fdividef(1.f, 1.f + __expf(-x1[j]));   // MUFU.RCP: the IEEE division made this kernel issue-bound
       const float sl = x1[j] * sg;
       d1[j] = g[j] * x2[j] * sg * (1.f + x1[j] * (1.f - sg));
       d2[j] = g[j] * sl;

@@ -33,6 +33,8 @@ constexpr int EPI_STAGE_BYTES = 4 * 32 * 64 * 4;  // 4 warps x (32 rows x 64 fp3
 struct GemmParams {
   CUtensorMap tmA, tmB;
   CUtensorMap tmD;  // bf16 output as {N, M}, box {64, 32}, 128B swizzle (TMA-store epilogues)
+  CUtensorMap tmAux;  // EV_SWIGLU_TMA: the pre-activation [M, N] (D is then [M, N/2])
+  int swiglu_half;    // N/2 in SwiGLU mode (B rows [0,N/2) = gate, [N/2,N) = up), else 0
   int M, N, K;
   int block_n, stages;
   int a_mn, b_mn;
@@ -137,7 +139,13 @@ __device__ __forceinline__ void epilogue8(const GemmParams& p, long long m, long
 // (all run-time flags resolved at compile time, full 8-column vectors, 16-byte aligned rows);
 // EV_GENERIC keeps every option behind run-time flags (tails, remap, SiLU, odd alignments).
 enum { EV_GENERIC = 0, EV_BF16 = 1, EV_BF16_BIAS = 2, EV_GATE = 3, EV_F32 = 4, EV_F32_ATOMIC = 5,
-       EV_BF16_TMA = 6 };
+       EV_BF16_TMA = 6, EV_SWIGLU_TMA = 7 };
+// EV_SWIGLU_TMA (CTA pairs only): B = xformers' w12 ([gate rows; up rows], MLP.py:19).  The leader
+// CTA stages 128 gate rows, its peer the matching 128 up rows, so every accumulator row holds
+// gate[128] | up[128] of the same hidden columns: the epilogue writes the pre-activation (aux,
+// bf16, needed by the backward) AND silu(gate) * up (D) -- the activation kernel and its re-read
+// of the 8d-wide pre-activation disappear.  The activation is computed from the bf16-rounded
+// pre-activation, i.e. bit-identical to mmdit_swiglu_fwd on the stored aux.
 // EV_BF16_TMA (bf16 output, optional fp32 bias): each epilogue thread owns one accumulator row
 // (its TMEM lane); a 64-column chunk is converted in registers, written as one 128-byte row of
 // a 128B-swizzled [32 x 64] bf16 staging tile (conflict-free 16-byte stores), and the tile leaves
@@ -312,7 +320,8 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
         const int tile = work / p.split_k, ks = work % p.split_k;
         const int m_blk = PAIR ? (tile % p.tiles_m) * 2 + (int)rank : tile % p.tiles_m;  // 128-row units
         const int n_blk = tile / p.tiles_m;
-        const int n0 = n_blk * block_n + (int)rank * (PAIR ? b_rows : 0);
+        const int n0 = p.swiglu_half ? n_blk * b_rows + (int)rank * p.swiglu_half
+                                     : n_blk * block_n + (int)rank * (PAIR ? b_rows : 0);
         const int kb0 = ks * p.kb_per_split;
         const int kb1 = min(kb0 + p.kb_per_split, p.kb_total);
         for (int kb = kb0; kb < kb1; ++kb) {
@@ -400,7 +409,70 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
       float* wbuf = reinterpret_cast<float*>(stage_buf + ew * (32 * 64 * 4));
       const int nchunks = block_n / 64;
       const int sub_row = lane >> 3, seg = lane & 7;
-      if constexpr (EV == EV_BF16_TMA) {
+      if constexpr (EV == EV_SWIGLU_TMA) {
+        uint8_t* sbase = stage_buf + ew * (32 * 64 * 4);
+        const float* bp = reinterpret_cast<const float*>(p.bias);
+        auto stage_tile = [&](const uint32_t (&packed)[32], const CUtensorMap* tm, int col) {
+          uint8_t* tile = sbase + (tma_buf & 1) * 4096;
+          if (lane == 0) tma_wait_group_read1();
+          __syncwarp();
+          uint8_t* prow = tile + lane * 128;
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<uint4*>(prow + ((j ^ (lane & 7)) << 4)) =
+                make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0 && !(p.debug & 1)) {
+            tma_store_2d(tm, tile, col, static_cast<int>(m0));
+            tma_commit_group();
+          }
+          ++tma_buf;
+        };
+        // bf16-round 64 accumulator columns (+bias) into 32 packed words
+        auto round64 = [&](const uint32_t (&lo)[32], const uint32_t (&hi)[32], int bias_col, uint32_t (&out)[32]) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const uint32_t* src = j < 8 ? &lo[4 * j] : &hi[4 * (j - 8)];
+            float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (bp) b = __ldg(reinterpret_cast<const float4*>(bp + bias_col + 4 * j));
+            out[2 * j] = pack_bf16x2(__uint_as_float(src[0]) + b.x, __uint_as_float(src[1]) + b.y);
+            out[2 * j + 1] = pack_bf16x2(__uint_as_float(src[2]) + b.z, __uint_as_float(src[3]) + b.w);
+          }
+        };
+        for (int c = 0; c < 2; ++c) {
+          const int n = n_blk * 128 + c * 64;   // column inside the gate (and the up) half
+          uint32_t gq[32], uq[32];
+          {
+            uint32_t r0[32], r1[32];
+            tmem_ld32(taddr + c * 64, r0);
+            tmem_ld32(taddr + c * 64 + 32, r1);
+            tmem_ld_wait();
+            round64(r0, r1, n, gq);
+            tmem_ld32(taddr + 128 + c * 64, r0);
+            tmem_ld32(taddr + 128 + c * 64 + 32, r1);
+            tmem_ld_wait();
+            round64(r0, r1, p.swiglu_half + n, uq);
+          }
+          if (c == 1) {  // accumulator drained: hand the TMEM stage back
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              if constexpr (PAIR) mbar_arrive_cluster(leader_tmem_empty + as * 8);
+              else mbar_arrive(&tmem_empty[as]);
+            }
+          }
+          if (m0 >= p.M) continue;
+          stage_tile(gq, &p.tmAux, n);
+          stage_tile(uq, &p.tmAux, p.swiglu_half + n);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float2 g = unpack_bf16x2(gq[j]), u = unpack_bf16x2(uq[j]);
+            gq[j] = pack_bf16x2(silu_f(g.x) * u.x, silu_f(g.y) * u.y);
+          }
+          stage_tile(gq, &p.tmD, n);
+        }
+      } else if constexpr (EV == EV_BF16_TMA) {
         uint8_t* sbase = stage_buf + ew * (32 * 64 * 4);   // two 4 KiB bf16 tiles (1024 B aligned)
         for (int c = 0; c < nchunks; ++c) {
           const int n = n_blk * block_n + c * 64;
@@ -508,7 +580,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
       as ^= 1;
       if (as == 0) aphase ^= 1;
     }
-    if constexpr (EV == EV_BF16_TMA) {
+    if constexpr (EV == EV_BF16_TMA || EV == EV_SWIGLU_TMA) {
       if (lane == 0) tma_wait_group0();  // staging tiles must outlive their stores
     }
   }
@@ -592,7 +664,8 @@ extern "C" int mmdit_gemm_bf16(const mmdit_gemm_args* a, void* stream_) {
                 (long long)a->lda, (long long)a->ldb);
   MMDIT_REQUIRE(!(a->accumulate && !a->d_fp32), MMDIT_ERR_ARG, "gemm: accumulate needs fp32 D");
   MMDIT_REQUIRE(a->epilogue == MMDIT_EPI_NONE || a->epilogue == MMDIT_EPI_GATE_RESID ||
-                    a->epilogue == MMDIT_EPI_SILU || a->epilogue == MMDIT_EPI_RESID,
+                    a->epilogue == MMDIT_EPI_SILU || a->epilogue == MMDIT_EPI_RESID ||
+                    a->epilogue == MMDIT_EPI_SWIGLU,
                 MMDIT_ERR_UNSUPPORTED, "gemm: epilogue %d not supported", a->epilogue);
   if (a->epilogue == MMDIT_EPI_GATE_RESID)
     MMDIT_REQUIRE(a->gate && a->rows_per_gate > 0 && a->resid, MMDIT_ERR_ARG,
@@ -600,6 +673,16 @@ extern "C" int mmdit_gemm_bf16(const mmdit_gemm_args* a, void* stream_) {
   if (a->epilogue == MMDIT_EPI_RESID)
     MMDIT_REQUIRE(a->resid != nullptr, MMDIT_ERR_ARG, "gemm: resid epilogue needs resid");
 
+  const bool swiglu = a->epilogue == MMDIT_EPI_SWIGLU;
+  if (swiglu) {
+    auto al = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+    MMDIT_REQUIRE(a->aux && !a->d_fp32 && !a->accumulate && a->split_k <= 1 && a->remap_rows == 0 &&
+                      a->b_major == 0 && a->N % 256 == 0 && a->M > BLOCK_M && al(a->D) && al(a->aux) &&
+                      a->ldd % 8 == 0 && a->ld_aux % 8 == 0 && (!a->bias || (a->bias_fp32 && al(a->bias))),
+                  MMDIT_ERR_UNSUPPORTED,
+                  "gemm: the SwiGLU epilogue needs aux, bf16 D [M,N/2], K-major B, N %% 256 == 0, M > 128, "
+                  "16-byte aligned rows and an fp32 bias");
+  }
   const int sms = num_sms();
   GemmParams p;
   memset(&p, 0, sizeof(p));
@@ -609,7 +692,7 @@ extern "C" int mmdit_gemm_bf16(const mmdit_gemm_args* a, void* stream_) {
   // split-K GEMMs (explicit slices / fp32 accumulate) fill the machine through the split, not through
   // narrower tiles: the split planners (here and ops._plan_split) assume 128x256 tiles
   const bool will_split = a->split_k > 1 || (a->split_k <= 0 && a->accumulate && a->d_fp32 && a->K >= 8 * BLOCK_K);
-  p.block_n = a->force_block_n ? a->force_block_n
+  p.block_n = swiglu ? 256 : a->force_block_n ? a->force_block_n
               : (will_split && a->N > 128) ? 256 : pick_block_n(a->M, a->N, sms);
   MMDIT_REQUIRE(p.block_n == 64 || p.block_n == 128 || p.block_n == 256, MMDIT_ERR_ARG,
                 "gemm: block_n %d", p.block_n);
@@ -619,7 +702,7 @@ extern "C" int mmdit_gemm_bf16(const mmdit_gemm_args* a, void* stream_) {
     const char* e = getenv("MMDIT_GEMM_PAIR");
     env_pair = e ? atoi(e) : 1;
   }
-  const bool pair = env_pair && p.block_n == 256 && a->M > BLOCK_M && !(a->reserved & 16);
+  const bool pair = swiglu || (env_pair && p.block_n == 256 && a->M > BLOCK_M && !(a->reserved & 16));
   const int workers = pair ? sms / 2 : sms;  // persistent work units running concurrently
   const int stage_bytes = A_STAGE_BYTES + (pair ? p.block_n / 2 : p.block_n) * BLOCK_K * 2;
   p.stages = (SMEM_BUDGET - 1024 - BAR_BYTES - EPI_STAGE_BYTES) / stage_bytes;
@@ -633,7 +716,8 @@ extern "C" int mmdit_gemm_bf16(const mmdit_gemm_args* a, void* stream_) {
     if (env_stages > 0 && p.stages > env_stages) p.stages = env_stages;
   }
   p.tiles_m = pair ? (p.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M) : (p.M + BLOCK_M - 1) / BLOCK_M;
-  p.tiles_n = (p.N + p.block_n - 1) / p.block_n;
+  p.tiles_n = (p.N + p.block_n - 1) / p.block_n;   // SwiGLU: N/256 tiles of 128 gate + 128 up columns
+  p.swiglu_half = swiglu ? p.N / 2 : 0;
   p.kb_total = (p.K + BLOCK_K - 1) / BLOCK_K;
   int split = a->split_k;
   const int tiles = p.tiles_m * p.tiles_n;
@@ -701,7 +785,9 @@ extern "C" int mmdit_gemm_bf16(const mmdit_gemm_args* a, void* stream_) {
                       (a->d_fp32 ? a->ldd % 4 == 0 : a->ldd % 8 == 0);
   const bool bias_ok = !a->bias || (a->bias_fp32 && al16(a->bias));
   int ev = EV_GENERIC;
-  if (vec_ok) {
+  if (swiglu) {
+    ev = EV_SWIGLU_TMA;
+  } else if (vec_ok) {
     if (a->d_fp32) {
       if (a->epilogue == MMDIT_EPI_NONE && !a->bias && !a->aux) {
         if (!a->accumulate) ev = EV_F32;
@@ -724,11 +810,17 @@ extern "C" int mmdit_gemm_bf16(const mmdit_gemm_args* a, void* stream_) {
   }
   MMDIT_REQUIRE(p.slice_stride == 0 || ev == EV_F32, MMDIT_ERR_ALIGN,
                 "gemm: split-K slices mode needs N %% 8 == 0 and 16-byte aligned D");
-  if (ev == EV_BF16_TMA) {
-    uint64_t dims[2] = {(uint64_t)a->N, (uint64_t)a->M}, strides[1] = {(uint64_t)a->ldd * 2};
+  if (ev == EV_BF16_TMA || ev == EV_SWIGLU_TMA) {
+    uint64_t dims[2] = {(uint64_t)(swiglu ? a->N / 2 : a->N), (uint64_t)a->M}, strides[1] = {(uint64_t)a->ldd * 2};
     uint32_t box[2] = {64, 32};
     int rc_d = encode_tmap(&p.tmD, a->D, 2, dims, strides, box, 2, true);
     if (rc_d) return rc_d;
+    if (swiglu) {
+      dims[0] = (uint64_t)a->N;
+      strides[0] = (uint64_t)a->ld_aux * 2;
+      rc_d = encode_tmap(&p.tmAux, a->aux, 2, dims, strides, box, 2, true);
+      if (rc_d) return rc_d;
+    }
   }
   int rc = 0;
 #define LAUNCH_EV(EVV)                                                                 \
@@ -744,6 +836,9 @@ extern "C" int mmdit_gemm_bf16(const mmdit_gemm_args* a, void* stream_) {
     LAUNCH_EV(EV_F32)
     LAUNCH_EV(EV_F32_ATOMIC)
     LAUNCH_EV(EV_BF16_TMA)
+    case EV_SWIGLU_TMA:
+      rc = launch_variant<EV_SWIGLU_TMA, true>(grid, smem_bytes, stream, p);
+      break;
   }
 #undef LAUNCH_EV
   if (rc) return rc;

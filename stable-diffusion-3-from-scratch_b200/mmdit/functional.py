@@ -18,6 +18,8 @@ from .ops import BF16, F32
 
 # MMDIT_FUSED_GATE=1 routes gate*x+residual through the GEMM epilogue instead of a separate kernel
 FUSED_GATE_EPILOGUE = os.environ.get("MMDIT_FUSED_GATE", "0") == "1"
+# MMDIT_FUSED_SWIGLU=0 keeps silu(x1)*x2 in its own kernel instead of the w12 GEMM's epilogue
+FUSED_SWIGLU = os.environ.get("MMDIT_FUSED_SWIGLU", "1") == "1"
 
 
 def _wgrad_slot(params):
@@ -390,8 +392,15 @@ class SwiGLUHiddenFn(Function):
     @staticmethod
     def forward(ctx, x, wb, w12, b12):
         x2 = x.reshape(-1, x.shape[-1])
-        h12 = ops.gemm(x2, wb, bias=None if b12 is None else b12.detach())
-        a = ops.swiglu_fwd(h12)
+        bias = None if b12 is None else b12.detach()
+        if FUSED_SWIGLU and x2.shape[0] > 128 and wb.shape[0] % 256 == 0 and (bias is None or bias.dtype == F32):
+            # activation in the GEMM epilogue: the [R, 8d] pre-activation is written once (for the
+            # backward) and never re-read by a separate activation kernel
+            h12 = torch.empty((x2.shape[0], wb.shape[0]), device=x.device, dtype=BF16)
+            a = ops.gemm(x2, wb, bias=bias, epilogue=ops.EPI_SWIGLU, aux=h12)
+        else:
+            h12 = ops.gemm(x2, wb, bias=bias)
+            a = ops.swiglu_fwd(h12)
         ctx.save_for_backward(x2, wb, h12)
         ctx.wparam = w12
         ctx.meta = (x.shape, b12 is not None)

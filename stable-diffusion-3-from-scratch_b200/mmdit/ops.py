@@ -10,7 +10,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import EPI_GATE_RESID, EPI_NONE, EPI_RESID, EPI_SILU  # noqa: F401
+from ._lib import EPI_GATE_RESID, EPI_NONE, EPI_RESID, EPI_SILU, EPI_SWIGLU  # noqa: F401
 
 BF16 = torch.bfloat16
 F32 = torch.float32
@@ -107,12 +107,14 @@ def _gemm(A, B, *, a_major=0, b_major=0, out=None, out_dtype=BF16, accumulate=Fa
             return out
     if dst is not None:
         out = dst
+    if epilogue == EPI_SWIGLU and aux is None:
+        raise ValueError("gemm: the SwiGLU epilogue needs aux (the [M, N] pre-activation output)")
     if out is None:
         rows = out_rows if out_rows is not None else M
         if remap is not None and out_rows is None:
             raise ValueError("gemm: remap needs out_rows or out")
         out = (torch.zeros if (accumulate or remap is not None) else torch.empty)(
-            (rows, N), device=A.device, dtype=out_dtype)
+            (rows, N // 2 if epilogue == EPI_SWIGLU else N), device=A.device, dtype=out_dtype)
     _rowmajor2d(out, "out")
     a = _lib.GemmArgs()
     a.A, a.B, a.D = A.data_ptr(), B.data_ptr(), out.data_ptr()

@@ -159,6 +159,48 @@ def group_epi():
     return ok
 
 
+def group_swiglu():
+    """Fused SwiGLU epilogue == plain GEMM followed by mmdit_swiglu_fwd, bit for bit."""
+    sys.path.insert(0, os.path.join(ROOT, "stable-diffusion-3-from-scratch_b200"))
+    from mmdit import ops
+    ok = True
+    for (M, d) in [(616, 256), (16384, 768), (9856, 768), (300, 128)]:
+        torch.manual_seed(M)
+        x = torch.randn(M, d, device=dev).bfloat16()
+        w = (torch.randn(8 * d, d, device=dev) / d ** 0.5).bfloat16()
+        b = torch.randn(8 * d, device=dev)
+        h_ref = ops.gemm(x, w, bias=b)
+        a_ref = ops.swiglu_fwd(h_ref)
+        h = torch.full((M, 8 * d), float("nan"), device=dev, dtype=torch.bfloat16)
+        a = ops.gemm(x, w, bias=b, epilogue=ops.EPI_SWIGLU, aux=h)
+        torch.cuda.synchronize()
+        same_h = bool((h == h_ref).all()) and not bool(torch.isnan(h.float()).any())
+        same_a = bool((a == a_ref).all())
+        t_ref = h_ref.float()
+        tor = torch.nn.functional.silu(t_ref[:, :4 * d]) * t_ref[:, 4 * d:]
+        rel = float((a.float() - tor).abs().max() / tor.abs().max())
+        print(f"[swiglu M={M} d={d}] pre-activation identical: {same_h}, activation identical: {same_a}, vs torch rel {rel:.2e}")
+        ok &= same_h and same_a and rel < 1e-2
+    for (M, d) in [(16384, 768), (9856, 768), (16384, 1536)]:
+        x = torch.randn(M, d, device=dev).bfloat16(); w = torch.randn(8 * d, d, device=dev).bfloat16(); b = torch.randn(8 * d, device=dev)
+        h = torch.empty((M, 8 * d), device=dev, dtype=torch.bfloat16)
+        def t(fn, iters=10):
+            for _ in range(2): fn()
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                for _ in range(iters): fn()
+            g.replay(); torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); g.replay(); e1.record(); torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / iters * 1e3
+        fused = t(lambda: ops.gemm(x, w, bias=b, epilogue=ops.EPI_SWIGLU, aux=h))
+        plain = t(lambda: ops.gemm(x, w, bias=b))
+        both = t(lambda: ops.swiglu_fwd(ops.gemm(x, w, bias=b)))
+        print(f"[swiglu perf M={M} d={d}] fused {fused:.1f} us | plain GEMM {plain:.1f} us | GEMM + activation kernel {both:.1f} us")
+    return ok
+
+
 def group_perf():
     shapes = [
         ("qkv_x cfg2", 16384, 2304, 768, 0, 0, False),
@@ -208,6 +250,6 @@ if __name__ == "__main__":
     g = sys.argv[1] if len(sys.argv) > 1 else "basic"
     _lib.check(L.mmdit_device_check(), "device_check")
     t0 = time.time()
-    ok = {"basic": group_basic, "major": group_major, "epi": group_epi, "perf": group_perf}[g]()
+    ok = {"basic": group_basic, "major": group_major, "epi": group_epi, "perf": group_perf, "swiglu": group_swiglu}[g]()
     print(f"GROUP {g}: {'ALL PASS' if ok else 'SOME FAIL'} ({time.time() - t0:.1f}s)")
     sys.exit(0 if ok else 1)

@@ -161,6 +161,9 @@ def instrument_kernels(trainer, batch):
     ops.attn_bwd = timed("attn_bwd", orig[2],
                          lambda q, k, v, o, l, do, dq, dk, dv, B, H, N, M, s: 10.0 * B * H * (N + M) ** 2 * 64)
     import mmdit.functional as Fn
+    from mmdit import streams
+    dual = streams.ENABLED
+    streams.ENABLED = False    # one stream: an event pair must time its kernel alone, not a neighbour too
     try:
         trainer._zero()
         torch.cuda._sleep(int(4e8))   # keep the GPU busy while the host enqueues: events then time kernels, not launch gaps
@@ -168,6 +171,7 @@ def instrument_kernels(trainer, batch):
         torch.cuda.synchronize()
     finally:
         ops.gemm, ops.attn_fwd, ops.attn_bwd = orig
+        streams.ENABLED = dual
     out = {}
     for kind, items in rec.items():
         ms = sum(e0.elapsed_time(e1) for e0, e1, _ in items)
@@ -284,12 +288,19 @@ def run_product(args):
     att_ms = kern["attn_fwd"]["ms"] + kern["attn_bwd"]["ms"]
     att_tf = (kern["attn_fwd"]["flops"] + kern["attn_bwd"]["flops"]) / (att_ms * 1e-3) / 1e12 if att_ms else 0.0
     step_ms = ms / args.steps
+    traffic = None   # dram__bytes_read+write per GEMM launch, from the committed ncu capture of this step
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_kernel_metrics_v6.json")) as f:
+            traffic = json.load(f)["gemm_tcgen05_kernel"]["dram_bytes_per_launch"]
+    except Exception:  # noqa: BLE001
+        pass
     roofline = {
         "bound": "tensor", "kernel": "gemm_tcgen05_kernel",
         "achieved": gemm_tf, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
         "frac": gemm_tf / pk["tf_sustained"], "peak_source": pk["src"] + " (sustained cuBLAS bf16)",
         "launches_per_step": g["launches"], "avg_launch_us": 1e3 * g["ms"] / max(1, g["launches"]),
-        "share_of_step": g["ms"] / step_ms, "traffic": None,
+        "share_of_step": g["ms"] / step_ms, "traffic": traffic,
+        "traffic_source": "profiles/r01_kernel_metrics_v6.json (ncu, mean over the step's 340 GEMM launches)",
         "algorithmic_flops_per_step": g["flops"],
         "attention": {"achieved": att_tf, "unit": "TFLOP/s", "frac": att_tf / pk["tf_sustained"],
                       "ms_per_step": att_ms, "share_of_step": att_ms / step_ms},
@@ -316,6 +327,7 @@ def run_product(args):
                                "rectified-flow train step incl. clip+AdamW (BASELINE configs[1])",
                    "global_batch": world * BATCH, "batch_per_gpu": BATCH, "parallelism": f"dp{world}",
                    "cuda_graph": bool(trainer.use_graph), "gradient_exchange": exchange,
+                   "two_stream_blocks": bool(__import__("mmdit.streams").streams.ENABLED),
                    "l2": "per-step working set (>20 GB) exceeds the 126 MB L2; no explicit flush"},
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "last_loss": losses[-1]},

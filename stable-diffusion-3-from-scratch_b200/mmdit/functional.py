@@ -12,7 +12,7 @@ import os
 import torch
 from torch.autograd import Function
 
-from . import ops
+from . import ops, streams
 from .ops import BF16, F32
 
 
@@ -41,6 +41,21 @@ def _wgrad_slot(params):
     rows = sum(p.shape[0] for p in params)
     K = params[0][0].numel()
     return torch.as_strided(slots[0], (rows, K), (K, 1), slots[0].storage_offset())
+
+
+def _wgrad_gemm(dy2, x2, params):
+    """dW = dY^T X (fp32), written into the parameters' gradient-bucket slot when they have one.
+    Under the trainer (streams.async_wgrad) the GEMM runs on the weight-gradient stream: nothing
+    in the backward depends on it, so the data-gradient chain goes on without waiting."""
+    out = _wgrad_slot(params)
+    if not (streams.async_wgrad and dy2.is_cuda):
+        return ops.gemm(dy2, x2, a_major=1, b_major=1, out_dtype=F32, out=out)
+    ws = streams.wgrad(dy2.device)
+    ws.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(ws):
+        dw = ops.gemm(dy2, x2, a_major=1, b_major=1, out_dtype=F32, out=out)
+    streams.keepalive.append((dy2, x2))
+    return dw
 
 
 def _split_rows(t, sizes):
@@ -84,7 +99,7 @@ class LinearFn(Function):
         dx = None
         if ctx.needs_input_grad[0]:
             dx = ops.gemm(dy2, wb, b_major=1).reshape(xshape)
-        dw = ops.gemm(dy2, x2, a_major=1, b_major=1, out_dtype=F32, out=_wgrad_slot(ctx.wparams))
+        dw = _wgrad_gemm(dy2, x2, ctx.wparams)
         grads = [g.view(shp) for g, shp in zip(_split_rows(dw, sizes), ctx.wshapes)]
         if has_bias:
             grads += list(_split_rows(ops.colsum(dy2), sizes))
@@ -125,7 +140,7 @@ class GatedLinearFn(Function):
         dab = torch.empty((Bn, n), device=do.device, dtype=F32) if ctx.has_bias else None
         da = ops.gate_bwd(do, aux, gate, dgate, dab, rpb)
         dx = ops.gemm(da, wb, b_major=1)
-        dw = ops.gemm(da, a, a_major=1, b_major=1, out_dtype=F32, out=_wgrad_slot([ctx.wparam])).view(ctx.wparam.shape)
+        dw = _wgrad_gemm(da, a, [ctx.wparam]).view(ctx.wparam.shape)
         db = dab.sum(0) if ctx.has_bias else None
         return dx, None, None, dgate, do, None, dw, db
 
@@ -413,7 +428,7 @@ class SwiGLUHiddenFn(Function):
         db = torch.zeros(h12.shape[1], device=da.device, dtype=F32) if has_bias else None
         dh = ops.swiglu_bwd(da.reshape(-1, da.shape[-1]).contiguous(), h12, db)
         dx = ops.gemm(dh, wb, b_major=1).reshape(xshape)
-        dw = ops.gemm(dh, x2, a_major=1, b_major=1, out_dtype=F32, out=_wgrad_slot([ctx.wparam]))
+        dw = _wgrad_gemm(dh, x2, [ctx.wparam])
         return dx, None, dw, db
 
 

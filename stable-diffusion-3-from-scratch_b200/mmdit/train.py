@@ -16,7 +16,7 @@ torch.distributed collectives (NCCL / gloo) remain as the fallback exchange (`pe
 import torch
 import torch.distributed as dist
 
-from . import ops
+from . import ops, streams
 from .functional import rf_loss
 from .optim import FusedAdamW
 
@@ -129,6 +129,8 @@ class GradBuckets:
         if p.grad is None:
             slot.zero_()
         elif p.grad.data_ptr() != slot.data_ptr():
+            if streams.async_wgrad and p.dim() >= 2:   # may still be in flight on the wgrad stream
+                streams.join_wgrad(p.device)
             slot.copy_(p.grad)
             self.copied_elems += p.numel()
         else:
@@ -148,6 +150,7 @@ class GradBuckets:
         self._count = [0] * len(self.buckets)
         self._works = [None] * len(self.buckets)
         self._seen = set()
+        self._hook_streams = [set() for _ in self.buckets]
         self.direct_elems = self.copied_elems = 0     # gradients written in place / copied into their slot
         if self.arena is not None:
             # the stream the backward runs on (inside a capture: the capturing stream); the hooks
@@ -158,10 +161,18 @@ class GradBuckets:
         if self.arena is not None:
             # fork: the side stream picks up after everything issued so far (this bucket's
             # gradients), then runs the bucket's exchange kernel next to the rest of the backward
-            main = self.main_stream or torch.cuda.current_stream()
-            ev = torch.cuda.Event()
-            ev.record(main)
-            self.side.wait_event(ev)
+            # (the gradients of a bucket may come from the caller's stream, from the text-branch
+            # stream of the two-stream block schedule, and from the stream a hook copied on)
+            srcs = {self.main_stream or torch.cuda.current_stream(), torch.cuda.current_stream()}
+            srcs |= self._hook_streams[bi]
+            if streams.ENABLED:
+                srcs.add(streams.side(self.side.device))
+            if streams.async_wgrad:
+                srcs.add(streams.wgrad(self.side.device))
+            for st in srcs:
+                ev = torch.cuda.Event()
+                ev.record(st)
+                self.side.wait_event(ev)
             off, n = self.ranges[bi]
             self.arena.all_reduce_mean(off, n, stream=self.side)
             self._works[bi] = True
@@ -173,6 +184,8 @@ class GradBuckets:
         with torch.no_grad():
             self._adopt(p)
         self._seen.add(id(p))
+        if self.arena is not None:
+            self._hook_streams[bi].add(torch.cuda.current_stream())
         self._count[bi] += 1
         if self.overlap and self.world_size > 1 and self._count[bi] == len(self.buckets[bi][2]):
             self._launch(bi)
@@ -287,7 +300,14 @@ class RFTrainer:
         x_t = ops.rf_noise(b["x0"], eps, b["t"])                      # :238
         v = self.model(x_t, b["t"], b["c"], b["pooled"], b["null_pooled"], b["null_gemma"], b["null_bert"])
         loss = rf_loss(v, eps, b["x0"])                               # model_trainer.py:429-446
-        loss.backward()
+        streams.keepalive.clear()          # operands of the previous step's weight-gradient GEMMs
+        streams.async_wgrad = streams.ASYNC_WGRAD and loss.is_cuda
+        try:
+            loss.backward()
+        finally:
+            streams.async_wgrad = False
+        if loss.is_cuda:
+            streams.join_wgrad(loss.device)   # weight gradients are complete for whoever reads them next
         return loss.detach()
 
     def _update(self):

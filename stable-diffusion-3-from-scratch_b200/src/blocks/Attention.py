@@ -70,12 +70,20 @@ class Attention(nn.Module):
         x [B,N,d], c [B,M,d] -> (a_x [B*N,d], a_c [B*M,d]) bf16."""
         B, N, d = x.shape
         M = c.shape[1]
-        x = x if x.dtype == BF16 else x.to(BF16)
-        c = c if c.dtype == BF16 else c.to(BF16)
-        wx = [self.query_proj_x.weight, self.key_proj_x.weight, self.value_proj_x.weight]
-        wc = [self.query_proj_c.weight, self.key_proj_c.weight, self.value_proj_c.weight]
-        qkv_x = LinearFn.apply(x.reshape(B * N, d), packed_weight(self, "qkv_x", wx), None, 0, 3, *wx)
-        qkv_c = LinearFn.apply(c.reshape(B * M, d), packed_weight(self, "qkv_c", wc), None, 0, 3, *wc)
+        return self.attend_qkv(self.project_qkv(x, "x"), self.project_qkv(c, "c"), orig_shape, B, N, M)
+
+    def project_qkv(self, t, which):
+        """Packed q|k|v projection of one stream ("x": image tokens, "c": text tokens) -> [B*T, 3d]."""
+        B, T, d = t.shape
+        t = t if t.dtype == BF16 else t.to(BF16)
+        if which == "x":
+            ws = [self.query_proj_x.weight, self.key_proj_x.weight, self.value_proj_x.weight]
+        else:
+            ws = [self.query_proj_c.weight, self.key_proj_c.weight, self.value_proj_c.weight]
+        return LinearFn.apply(t.reshape(B * T, d), packed_weight(self, "qkv_" + which, ws), None, 0, 3, *ws)
+
+    def attend_qkv(self, qkv_x, qkv_c, orig_shape, B, N, M):
+        """QK-norm + RoPE + joint attention on the packed projections of both streams."""
         cos = sin = None
         if self.positional_encoding == "RoPE2d":
             # patch size 2 is hard-coded in the reference as well (Attention.py:178-179)

@@ -12,7 +12,7 @@ instead of recomputed (180 GB of HBM3e makes recompute a pure loss at these size
 import torch
 from torch import nn
 
-from mmdit import ops
+from mmdit import ops, streams
 from mmdit.functional import GatedLinearFn, LinearFn
 from mmdit.shadow import packed_weight
 from src.blocks.Attention import Attention
@@ -101,21 +101,54 @@ class Transformer_Block_Dual(nn.Module):
 
         # modulate_keep returns (LN-mod(X), X): taking the residual from the second output lets the LN
         # backward kernel add the residual-path gradient itself (no separate elementwise add)
+        if streams.active(X):
+            return self._forward_two_streams(X, c, m, orig_shape, B, N, M)
         xn, X = modulate_keep(X, m[0], m[1])
         if self.last:
             cn = modulate(c, m[2], m[3])
         else:
             cn, c = modulate_keep(c, m[2], m[3])
         a_x, a_c = self.attn.attend(xn, cn, orig_shape)
-        X = self._gated(a_x, self.attn.out_proj_x, m[4], X, N)
+        X = self._x_branch(a_x, X, m, B, N)
         if not self.last:
-            c = self._gated(a_c, self.attn.out_proj_c, m[8], c, M)
+            c = self._c_branch(a_c, c, m, B, M)
+        return X, c
 
+    def _x_branch(self, a_x, X, m, B, N):
+        """Image stream after the attention: out-projection, gate, MLP, gate."""
+        X = self._gated(a_x, self.attn.out_proj_x, m[4], X, N)
         mx = self._swiglu(self.MLP_x)
         xn, X = modulate_keep(X, m[5], m[6])
-        X = self._gated(mx.hidden(xn).reshape(B * N, -1), mx.w3, m[7], X, N)
+        return self._gated(mx.hidden(xn).reshape(B * N, -1), mx.w3, m[7], X, N)
+
+    def _c_branch(self, a_c, c, m, B, M):
+        """Text stream after the attention (absent in the last block)."""
+        c = self._gated(a_c, self.attn.out_proj_c, m[8], c, M)
+        mc = self._swiglu(self.MLP_c)
+        cn, c = modulate_keep(c, m[9], m[10])
+        return self._gated(mc.hidden(cn).reshape(B * M, -1), mc.w3, m[11], c, M)
+
+    def _forward_two_streams(self, X, c, m, orig_shape, B, N, M):
+        """Same math, text branch on the side stream (mmdit/streams.py): the branches only meet at
+        the joint attention, so each block is fork -> [LN+QKV] x2 -> join -> attention -> fork."""
+        main = torch.cuda.current_stream()
+        side = streams.side(X.device)
+        side.wait_stream(main)                      # modulation (and the incoming c) are ready
+        with torch.cuda.stream(side):
+            if self.last:
+                cn = modulate(c, m[2], m[3])
+            else:
+                cn, c = modulate_keep(c, m[2], m[3])
+            qkv_c = self.attn.project_qkv(cn, "c")
+        xn, X = modulate_keep(X, m[0], m[1])
+        qkv_x = self.attn.project_qkv(xn, "x")
+        main.wait_stream(side)                      # text q|k|v ready
+        a_x, a_c = self.attn.attend_qkv(qkv_x, qkv_c, orig_shape, B, N, M)
         if not self.last:
-            mc = self._swiglu(self.MLP_c)
-            cn, c = modulate_keep(c, m[9], m[10])
-            c = self._gated(mc.hidden(cn).reshape(B * M, -1), mc.w3, m[11], c, M)
+            side.wait_stream(main)                  # attention output ready
+            with torch.cuda.stream(side):
+                c = self._c_branch(a_c, c, m, B, M)
+        X = self._x_branch(a_x, X, m, B, N)
+        if self.last:
+            main.wait_stream(side)                  # nothing of the text branch is left in flight
         return X, c

@@ -16,7 +16,7 @@ import numpy as np
 import torch
 from torch import nn
 
-from mmdit import ops
+from mmdit import ops, streams
 from mmdit.functional import LinearFn, TextFrontFn, UnpatchifyFn
 from mmdit.shadow import packed_weight
 from src.blocks.ImagePositionalEncoding import PatchEmbed
@@ -175,6 +175,8 @@ class diff_model(nn.Module):
         yps = yp_all.unflatten(1, (len(yws), self.dim)).unbind(1)
         for block, yp in zip(self.blocks, yps):
             x, cseq = block(x, cseq, y, orig_shape, yp=yp)
+        if streams.active(x):   # two-stream block schedule: the text branch must not outlive the forward
+            torch.cuda.current_stream().wait_stream(streams.side(x.device))
 
         # output head (:339,342)
         x = self._linear(self.out_proj, self.out_norm(x, y))

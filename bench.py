@@ -26,6 +26,17 @@ CFG2 = dict(inCh=16, class_dim=768, patch_size=2, dim=768, hidden_scale=4.0, num
             attn_type="softmax_flash", MLP_type="swiglu", num_blocks=12, positional_encoding="RoPE2d")
 LATENT, TEXT_TOKENS, BATCH = 32, 154, 64
 METRIC, UNIT = "mmdit_train_images_per_sec_256px", "images/s"
+# --config: the other BASELINE training configurations (parity-test shapes; NOT the bench line the
+# metric is quoted on, which stays cfg2).  name -> (model overrides, latent side, batch per GPU, label)
+CONFIGS = {
+    "cfg2": (dict(), 32, 64, "MMDiT depth12/dim768/12 heads, 256px (32x32x16 latent, 256+154 tokens), "
+                             "rectified-flow train step incl. clip+AdamW (BASELINE configs[1])"),
+    "cfg3": (dict(dim=1536, num_heads=24, num_blocks=24), 32, 32,
+             "MMDiT depth24/dim1536/24 heads, 256px (256+154 tokens), train step (BASELINE configs[2])"),
+    "cfg4": (dict(dim=1536, num_heads=24, num_blocks=24), 64, 16,
+             "MMDiT depth24/dim1536/24 heads, 512px (64x64x16 latent, 1024+154 tokens), train step (BASELINE configs[3])"),
+}
+WORKLOAD = CONFIGS["cfg2"][3]
 
 
 def train_flops_per_image(cfg, N, M):
@@ -323,8 +334,7 @@ def run_product(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": "MMDiT depth12/dim768/12 heads, 256px (32x32x16 latent, 256+154 tokens), "
-                               "rectified-flow train step incl. clip+AdamW (BASELINE configs[1])",
+        "config": {"workload": WORKLOAD,
                    "global_batch": world * BATCH, "batch_per_gpu": BATCH, "parallelism": f"dp{world}",
                    "cuda_graph": bool(trainer.use_graph), "gradient_exchange": exchange,
                    "two_stream_blocks": bool(__import__("mmdit.streams").streams.ENABLED),
@@ -341,6 +351,16 @@ def run_product(args):
         dist.destroy_process_group()
 
 
+def select_config(name, batch):
+    """Point the module-level workload constants at one of CONFIGS."""
+    global CFG2, LATENT, BATCH, WORKLOAD, METRIC
+    over, LATENT, b, WORKLOAD = CONFIGS[name]
+    CFG2 = dict(CFG2, **over)
+    BATCH = batch or b
+    if name != "cfg2":
+        METRIC = f"mmdit_train_images_per_sec_{LATENT * 8}px_{name}"
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -351,7 +371,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="data-parallel gradient exchange: our peer-memory kernel (default) or NCCL")
+    ap.add_argument("--config", default="cfg2", choices=sorted(CONFIGS))
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the config's)")
     args = ap.parse_args()
+    select_config(args.config, args.batch)
     if args.warmup < 3:
         args.warmup = 3
     if args.impl == "reference":

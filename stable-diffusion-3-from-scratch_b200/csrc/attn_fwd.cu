@@ -13,8 +13,14 @@
 //   warps 2..5  softmax: one thread per query row (TMEM lane), online softmax in
 //               fp32 with exp2, P written as bf16 into 128B-swizzled smem (the A
 //               operand of the second MMA), O rescaled in TMEM.
+// Pipelining inside a CTA: a softmax thread turns its S row into packed bf16 REGISTERS; the
+// moment its last S column has left TMEM it signals `s_free`, and the MMA warp issues S of the
+// NEXT key tile while this tile's exponentials are still being computed; P is stored to smem only
+// after the previous P.V has retired, and that P.V overlaps the next tile's softmax math.
 // Tiles never straddle the image/text boundary: each stream is tiled
 // separately and partial tiles are masked, so any N, M work.
+#include <type_traits>
+
 #include "common.cuh"
 #include "mmdit_b200.h"
 
@@ -64,7 +70,8 @@ attn_fwd_kernel(const __grid_constant__ AttnFwdParams p) {
   uint64_t* s_full = bars + 5;
   uint64_t* p_full = bars + 6;
   uint64_t* pv_done = bars + 7;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* s_free = bars + 8;    // every softmax thread holds its S row in registers
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ntx = (p.N + ATT_TILE - 1) / ATT_TILE;
@@ -92,6 +99,7 @@ attn_fwd_kernel(const __grid_constant__ AttnFwdParams p) {
       mbar_init(s_full, 1);
       mbar_init(p_full, 128);
       mbar_init(pv_done, 1);
+      mbar_init(s_free, 128);
       mbar_fence_init();
       // fire Q and the first two K/V tiles right away: they fly while TMEM is allocated
       mbar_expect_tx(q_full, ATT_TILE_BYTES);
@@ -138,14 +146,16 @@ attn_fwd_kernel(const __grid_constant__ AttnFwdParams p) {
       TL(tls++, 2);
       mbar_wait(q_full, 0);
       TL(tls++, 3);
-      for (int j = 0; j < nkv; ++j) {
-        const int st = j & 1;
+      auto tile_cols = [&](int j) {   // key columns of tile j that exist, rounded up to the MMA N step
         const int ks = j < ntx ? 0 : 1;
         const int row0 = (ks == 0 ? j : j - ntx) * ATT_TILE;
         const int nv = min(ATT_TILE, (ks == 0 ? p.N : p.M) - row0);
-        const int n_mma = (nv + 15) & ~15;  // partial key tiles: only the columns that exist
-        const uint32_t idesc_s = make_idesc_bf16(128, n_mma, 0, 0);
-        const uint64_t k_desc = k_desc0 + st * kTile, v_desc = v_desc0 + st * kTile;
+        return (nv + 15) & ~15;
+      };
+      auto issue_s = [&](int j) {
+        const int st = j & 1;
+        const uint32_t idesc_s = make_idesc_bf16(128, tile_cols(j), 0, 0);
+        const uint64_t k_desc = k_desc0 + st * kTile;
         mbar_wait(&kv_full[st], (j >> 1) & 1);
         tc_fence_after();
         TL(tls++, 10 + j);
@@ -154,6 +164,17 @@ attn_fwd_kernel(const __grid_constant__ AttnFwdParams p) {
           umma_bf16(tmem_S, q_desc + k * kStepK, k_desc + k * kStepK, idesc_s, k > 0);
         umma_commit(s_full);
         TL(tls++, 20 + j);
+      };
+      issue_s(0);
+      for (int j = 0; j < nkv; ++j) {
+        const int st = j & 1;
+        const int n_mma = tile_cols(j);
+        const uint64_t v_desc = v_desc0 + st * kTile;
+        if (j + 1 < nkv) {
+          mbar_wait(s_free, j & 1);   // S_j sits in the softmax threads' registers: TMEM S is free
+          tc_fence_after();
+          issue_s(j + 1);
+        }
         mbar_wait(p_full, j & 1);
         tc_fence_after();
         TL(tls++, 30 + j);
@@ -203,7 +224,12 @@ attn_fwd_kernel(const __grid_constant__ AttnFwdParams p) {
       TL(tls++, 60 + j);
       if (!warp_active) {
         tc_fence_before();
+        mbar_arrive(s_free);
         mbar_arrive(p_full);
+        // stay in step with the working warps: S of the next tile is issued as soon as s_free
+        // completes, so without this wait an idle warp could see s_full(j+1) and arrive on p_full
+        // a second time while phase j is still open (the phase would complete without P_j)
+        mbar_wait(p_full, j & 1);
         continue;
       }
       float alpha = 1.f, mb, m_new = m;
@@ -232,12 +258,12 @@ attn_fwd_kernel(const __grid_constant__ AttnFwdParams p) {
         mb = bound_l2;   // fixed reference point: no running maximum, no rescale of O
       }
       TL(tls++, 70 + j);
-      if (j > 0) {
-        mbar_wait(pv_done, (j - 1) & 1);   // previous P V retired: sP is free (and O is final so far)
+      if (j > 0 && !use_bound) {
+        mbar_wait(pv_done, (j - 1) & 1);   // previous P V retired: O is final so far
         tc_fence_after();
         TL(tls++, 80 + j);
         // rescale O only if some row of this warp actually raised its maximum
-        if (!use_bound && !__all_sync(0xffffffffu, m_new == m)) {
+        if (!__all_sync(0xffffffffu, m_new == m)) {
 #pragma unroll
           for (int c = 0; c < 2; ++c) {
             uint32_t o[32];
@@ -251,51 +277,51 @@ attn_fwd_kernel(const __grid_constant__ AttnFwdParams p) {
         }
       }
       TL(tls++, 90 + j);
+      // P row of this thread as 64 packed bf16 pairs, kept in registers until the smem tile is free
+      uint32_t pk[64];
       float rs4[4] = {0.f, 0.f, 0.f, 0.f};
-      if (nv == ATT_TILE) {
-        // full key tile: no masking in the inner loop
-#pragma unroll 1
+      auto exp_row = [&](auto full_tag) {
+        constexpr bool FULL = decltype(full_tag)::value;
+#pragma unroll
         for (int c = 0; c < 4; ++c) {
-          uint32_t s[32];
-          tmem_ld32(tmem_S + lane_off + c * 32, s);
-          tmem_ld_wait();
-          uint8_t* prow = sP + (c >> 1) * ATT_TILE_BYTES + r * 128;
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            float e[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              e[i] = ex2_approx(fmaf(__uint_as_float(s[g * 8 + i]), sl2, -mb));
-              rs4[i & 3] += e[i];
+          if (FULL || c < nchunk) {
+            uint32_t sv[32];
+            tmem_ld32(tmem_S + lane_off + c * 32, sv);
+            tmem_ld_wait();
+            if (c == (FULL ? 3 : nchunk - 1)) {   // S has left TMEM: the next QK^T may overwrite it
+              tc_fence_before();
+              mbar_arrive(s_free);
             }
-            uint4 u;
-            u.x = pack_bf16x2(e[0], e[1]); u.y = pack_bf16x2(e[2], e[3]);
-            u.z = pack_bf16x2(e[4], e[5]); u.w = pack_bf16x2(e[6], e[7]);
-            *reinterpret_cast<uint4*>(prow + ((((c & 1) * 4 + g) ^ (r & 7)) << 4)) = u;
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              float e0 = ex2_approx(fmaf(__uint_as_float(sv[i]), sl2, -mb));
+              float e1 = ex2_approx(fmaf(__uint_as_float(sv[i + 1]), sl2, -mb));
+              if (!FULL) {
+                if (c * 32 + i >= nv) e0 = 0.f;
+                if (c * 32 + i + 1 >= nv) e1 = 0.f;
+              }
+              rs4[(i >> 1) & 3] += e0 + e1;
+              pk[c * 16 + (i >> 1)] = pack_bf16x2(e0, e1);
+            }
           }
         }
-      } else {
-#pragma unroll 1
-        for (int c = 0; c < nchunk; ++c) {
-          uint32_t s[32];
-          tmem_ld32(tmem_S + lane_off + c * 32, s);
-          tmem_ld_wait();
+      };
+      if (nv == ATT_TILE) exp_row(std::true_type{});
+      else exp_row(std::false_type{});
+      if (j > 0 && use_bound) {
+        mbar_wait(pv_done, (j - 1) & 1);   // previous P V retired: the P tile in smem is free
+        tc_fence_after();
+        TL(tls++, 80 + j);
+      }
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        if (c < nchunk) {
           uint8_t* prow = sP + (c >> 1) * ATT_TILE_BYTES + r * 128;
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            float e[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int col = c * 32 + g * 8 + i;
-              e[i] = col < nv ? ex2_approx(fmaf(__uint_as_float(s[g * 8 + i]), sl2, -mb)) : 0.f;
-              rs4[i & 3] += e[i];
-            }
-            uint4 u;
-            u.x = pack_bf16x2(e[0], e[1]); u.y = pack_bf16x2(e[2], e[3]);
-            u.z = pack_bf16x2(e[4], e[5]); u.w = pack_bf16x2(e[6], e[7]);
-            const int chunk16 = (c & 1) * 4 + g;  // 16-byte chunk inside the 128-byte row
-            *reinterpret_cast<uint4*>(prow + ((chunk16 ^ (r & 7)) << 4)) = u;
-          }
+          for (int g = 0; g < 4; ++g)
+            *reinterpret_cast<uint4*>(prow + ((((c & 1) * 4 + g) ^ (r & 7)) << 4)) =
+                make_uint4(pk[c * 16 + g * 4], pk[c * 16 + g * 4 + 1], pk[c * 16 + g * 4 + 2],
+                           pk[c * 16 + g * 4 + 3]);
         }
       }
       const float rs = (rs4[0] + rs4[1]) + (rs4[2] + rs4[3]);

@@ -28,6 +28,7 @@ def test_gemm_all_layouts_and_epilogues(dev):
     assert gemm_probe.group_basic()
     assert gemm_probe.group_major()
     assert gemm_probe.group_epi()
+    assert gemm_probe.group_swiglu()      # fused SwiGLU epilogue == GEMM + activation kernel, bit for bit
 
 
 def test_rowwise_kernels(dev):
@@ -43,6 +44,23 @@ def test_elementwise_kernels(dev):
 def test_joint_attention_fwd_bwd(dev):
     import kernel_probe
     assert kernel_probe.group_attn()
+
+
+def test_wide_512px_shape_trains_without_fault(dev):
+    """BASELINE configs[3] geometry (dim 1536, 24 heads, 64x64 latent -> 1024+154 tokens: 10 key
+    tiles and a 26-row last query tile) through the trainer, two blocks deep.  Regression test for
+    a barrier race in the attention forward that only showed inside the full model at this shape."""
+    from mmdit.train import RFTrainer, host_batch
+    from src.models.diff_model import diff_model
+    torch.manual_seed(0)
+    model = diff_model(inCh=16, class_dim=768, patch_size=2, dim=1536, hidden_scale=4.0, num_heads=24,
+                       attn_type="softmax_flash", MLP_type="swiglu", num_blocks=2,
+                       positional_encoding="RoPE2d", device=dev)
+    for use_graph in (False, True):
+        tr = RFTrainer(model, use_graph=use_graph)
+        losses = [float(tr.step(tr.to_device(host_batch(2, 16, 64, 64, 154, seed=7 + i)))) for i in range(3)]
+        torch.cuda.synchronize()
+        assert all(l == l and 0.5 < l < 5.0 for l in losses), losses
 
 
 def _run_model(cfg_model, B, h, w, M, dev, seed=1000):

@@ -104,6 +104,7 @@ def group_attn():
     ok &= attn_case(1, 2, 1024, 256)
     ok &= attn_case(2, 4, 256, 154, bounded=True)      # single-pass softmax against the QK-norm bound
     ok &= attn_case(2, 3, 240, 77, bounded=True)
+    ok &= attn_case(2, 4, 1024, 154, bounded=True)     # 10 key tiles, 26-row last query tile (idle softmax warps)
     return ok
 
 

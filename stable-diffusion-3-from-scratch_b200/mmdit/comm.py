@@ -6,6 +6,7 @@ then reduced by a single captured-in-graph kernel (csrc/comm.cu: reduce-scatter 
 mean over NVLink loads/stores).  torch.distributed is only the rendezvous here, not the data path.
 """
 import ctypes as C
+import os
 
 import torch
 import torch.distributed as dist
@@ -74,6 +75,7 @@ class PeerArena:
 
     def all_reduce_mean(self, offset, n, stream=None, ctas=0):
         """arena[offset:offset+n] <- mean over ranks (one kernel on `stream`, graph capturable)."""
+        ctas = ctas or int(os.environ.get("MMDIT_COMM_CTAS", "0"))
         s = stream.cuda_stream if stream is not None else torch.cuda.current_stream().cuda_stream
         _lib.check(_lib.lib().mmdit_allreduce_mean_f32(C.byref(self.comm), offset, n, ctas, s),
                    "mmdit_allreduce_mean_f32")

@@ -500,6 +500,7 @@ extern "C" int mmdit_attn_bwd(const mmdit_attn_args* a, void* stream_) {
     // delta = rowsum(dO * O)
     const long long nrows = (long long)a->B * rows[s];
     const long long work = nrows * a->H * 8;
+    MMDIT_CARVEOUT(attn_delta_kernel);
     attn_delta_kernel<<<(unsigned)((work + 255) / 256), 256, 0, stream>>>(
         static_cast<const bf16*>(a->o[s]), static_cast<const bf16*>(a->d_o[s]), a->delta, nrows,
         a->H, a->ld_o[s], a->ld_do[s], rows[s], s == 0 ? 0 : a->N, T);
@@ -529,6 +530,7 @@ extern "C" int mmdit_attn_bwd(const mmdit_attn_args* a, void* stream_) {
     const long long work = (long long)a->B * rows[s] * (dmodel / 8);
     long long blocks = (work + 255) / 256;
     if (blocks > num_sms() * 16LL) blocks = num_sms() * 16LL;
+    MMDIT_CARVEOUT(attn_dq_convert_kernel);
     attn_dq_convert_kernel<<<(unsigned)blocks, 256, 0, stream>>>(
         a->dq_acc, static_cast<bf16*>(a->dq[s]), a->B, T, s == 0 ? 0 : a->N, rows[s], dmodel,
         a->ld_dq[s]);

@@ -207,10 +207,10 @@ extern "C" int mmdit_allreduce_mean_f32(const mmdit_comm* c, int64_t offset, int
   if (ctas <= 0) ctas = 48;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   switch (c->world) {
-    case 1: allreduce_mean_kernel<1><<<ctas, COMM_THREADS, 0, s>>>(p); break;
-    case 2: allreduce_mean_kernel<2><<<ctas, COMM_THREADS, 0, s>>>(p); break;
-    case 4: allreduce_mean_kernel<4><<<ctas, COMM_THREADS, 0, s>>>(p); break;
-    case 8: allreduce_mean_kernel<8><<<ctas, COMM_THREADS, 0, s>>>(p); break;
+    case 1: MMDIT_CARVEOUT(allreduce_mean_kernel<1>); allreduce_mean_kernel<1><<<ctas, COMM_THREADS, 0, s>>>(p); break;
+    case 2: MMDIT_CARVEOUT(allreduce_mean_kernel<2>); allreduce_mean_kernel<2><<<ctas, COMM_THREADS, 0, s>>>(p); break;
+    case 4: MMDIT_CARVEOUT(allreduce_mean_kernel<4>); allreduce_mean_kernel<4><<<ctas, COMM_THREADS, 0, s>>>(p); break;
+    case 8: MMDIT_CARVEOUT(allreduce_mean_kernel<8>); allreduce_mean_kernel<8><<<ctas, COMM_THREADS, 0, s>>>(p); break;
     default:
       set_last_error("allreduce: world size %d not supported (1, 2, 4, 8)", c->world);
       return MMDIT_ERR_UNSUPPORTED;

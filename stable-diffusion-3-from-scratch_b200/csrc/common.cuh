@@ -36,6 +36,19 @@ int encode_tmap(CUtensorMap* map, const void* base, int rank, const uint64_t* di
                 const uint64_t* strides_bytes /* rank-1 entries */, const uint32_t* box,
                 int elem_bytes, bool swizzle128);
 int num_sms();
+// Ask for the maximum shared-memory carve-out for a kernel that itself needs (almost) none.
+// An SM runs CTAs of different kernels side by side only under ONE L1/shared split; the GEMM and
+// attention kernels need the 228 KB split, so a streaming / exchange kernel that keeps the default
+// split cannot share an SM with them (and, once resident, keeps their CTAs out).  With the same
+// preference the row kernels of one stream and the peer-memory exchange overlap the tensor-core
+// kernels of another.  An experiment knob: no effect was measurable at N = 1, so it is OFF unless
+// MMDIT_CARVEOUT=1 (multi-GPU overlap of the exchange kernel not yet measured with it).
+void prefer_max_smem_carveout(const void* kernel);
+#define MMDIT_CARVEOUT(kernel)                                                            \
+  do {                                                                                    \
+    static bool once_ = (mmdit::prefer_max_smem_carveout((const void*)(kernel)), true);   \
+    (void)once_;                                                                          \
+  } while (0)
 
 // ---------------------------------------------------------------- device ---
 #ifdef __CUDACC__

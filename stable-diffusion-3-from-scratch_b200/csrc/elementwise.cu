@@ -531,6 +531,7 @@ int mmdit_qknorm_rope_fwd(const void* qkv, const float* wq, const float* wk, con
                     ld_out % 8 == 0 && tokens_per_sample > 0 && (!rope_cos == !rope_sin),
                 MMDIT_ERR_ARG, "qknorm_rope_fwd: bad arguments (head_dim is fixed at 64)");
   const long long work = rows * (long long)(d / 8);
+  MMDIT_CARVEOUT(qknorm_rope_fwd_kernel);
   qknorm_rope_fwd_kernel<<<grid_for(work, 256), 256, 0, (cudaStream_t)stream>>>(
       (const bf16*)qkv, wq, wk, rope_cos, rope_sin, (bf16*)out, rows, d, ld_in, ld_out,
       tokens_per_sample, eps);
@@ -548,6 +549,7 @@ int mmdit_qknorm_rope_bwd(const void* dqk, const void* qkv, const float* wq, con
   unsigned grid = grid_for(work, 256);
   const unsigned cap = (unsigned)num_sms() * 4;  // fewer, longer-lived blocks: fewer atomics
   if (grid > cap) grid = cap;
+  MMDIT_CARVEOUT(qknorm_rope_bwd_kernel);
   qknorm_rope_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
       (const bf16*)dqk, (const bf16*)qkv, wq, wk, rope_cos, rope_sin, (bf16*)dqkv, dwq, dwk, rows,
       d, ld_g, ld_in, ld_dout, tokens_per_sample, eps);
@@ -561,6 +563,7 @@ int mmdit_gate_residual_fwd(const void* a, const void* gate, const void* resid, 
                     ld_gate % 8 == 0,
                 MMDIT_ERR_ARG, "gate_residual_fwd: bad arguments");
   const long long work = rows * (long long)(d / 8);
+  MMDIT_CARVEOUT(gate_residual_fwd_kernel);
   gate_residual_fwd_kernel<<<grid_for(work, 256), 256, 0, (cudaStream_t)stream>>>(
       (const bf16*)a, (const bf16*)gate, (const bf16*)resid, (bf16*)out, rows, d, rows_per_batch,
       ld_gate);
@@ -578,6 +581,7 @@ int mmdit_swiglu_fwd(const void* h12, void* a, int64_t rows, int32_t hidden, voi
   MMDIT_REQUIRE(h12 && a && rows > 0 && hidden > 0 && hidden % 8 == 0, MMDIT_ERR_ARG,
                 "swiglu_fwd: bad arguments");
   const long long work = rows * (long long)(hidden / 8);
+  MMDIT_CARVEOUT(swiglu_fwd_kernel);
   swiglu_fwd_kernel<<<grid_for(work, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)h12,
                                                                           (bf16*)a, rows, hidden);
   return check_launch("swiglu_fwd_kernel");
@@ -595,6 +599,7 @@ int mmdit_swiglu_bwd(const void* da, const void* h12, void* dh12, float* db12, f
   const int rpb = 64;
   const int nrb = (int)((rows + rpb - 1) / rpb);
   dim3 grid((unsigned)((hidden / 8 + 127) / 128), (unsigned)nrb);
+  MMDIT_CARVEOUT(swiglu_bwd_kernel);
   swiglu_bwd_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>((const bf16*)da, (const bf16*)h12,
                                                            (bf16*)dh12, db12 ? workspace : nullptr,
                                                            rows, hidden, rpb);
@@ -739,6 +744,7 @@ int mmdit_fold_slices_f32(const float* ws, float* out, int64_t n, int32_t slices
   MMDIT_REQUIRE(ws && out && n > 0 && n % 4 == 0 && slices > 0 && stride % 4 == 0 &&
                     ((uintptr_t)ws & 15) == 0 && ((uintptr_t)out & 15) == 0,
                 MMDIT_ERR_ARG, "fold_slices_f32: bad arguments");
+  MMDIT_CARVEOUT(fold_slices_kernel);
   fold_slices_kernel<<<grid_for(n / 4, 256), 256, 0, (cudaStream_t)stream>>>(ws, out, n, slices, stride,
                                                                              accumulate);
   return check_launch("fold_slices_kernel");

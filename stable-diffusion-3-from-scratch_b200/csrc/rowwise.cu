@@ -408,7 +408,7 @@ int mmdit_ln_modulate_fwd(const void* x, const void* shift, const void* scale, v
   MMDIT_REQUIRE(x && shift && scale && y && rows > 0 && d > 0 && d % 8 == 0 && rows_per_batch > 0,
                 MMDIT_ERR_ARG, "ln_modulate_fwd: bad arguments (d must be a multiple of 8)");
   const unsigned grid = (unsigned)((rows + ROW_WARPS - 1) / ROW_WARPS);
-  DISPATCH_NC(d, (ln_mod_fwd_kernel<NC><<<grid, ROW_THREADS, 0, (cudaStream_t)stream>>>(
+  DISPATCH_NC(d, MMDIT_CARVEOUT(ln_mod_fwd_kernel<NC>); (ln_mod_fwd_kernel<NC><<<grid, ROW_THREADS, 0, (cudaStream_t)stream>>>(
                      (const bf16*)x, (const bf16*)shift, (const bf16*)scale, (bf16*)y, mean, rstd,
                      rows, d, rows_per_batch, ld_mod, eps)));
   return check_launch("ln_mod_fwd_kernel");
@@ -433,10 +433,11 @@ int mmdit_ln_modulate_bwd(const void* dy, const void* x, const float* mean, cons
   const unsigned grid = (unsigned)(nb * bpb);
   const size_t smem = (size_t)BWD_WARPS * 2 * d * sizeof(float);
   MMDIT_REQUIRE(smem <= 48 * 1024, MMDIT_ERR_UNSUPPORTED, "ln_modulate_bwd: d=%d too wide", d);
-  DISPATCH_NC(d, (ln_mod_bwd_kernel<NC><<<grid, BWD_THREADS, smem, (cudaStream_t)stream>>>(
+  DISPATCH_NC(d, MMDIT_CARVEOUT(ln_mod_bwd_kernel<NC>); (ln_mod_bwd_kernel<NC><<<grid, BWD_THREADS, smem, (cudaStream_t)stream>>>(
                      (const bf16*)dy, (const bf16*)x, mean, rstd, (const bf16*)scale,
                      (const bf16*)dres, (bf16*)dx, workspace, d, rows_per_batch, ld_mod, rpb, bpb)));
   dim3 g2((2 * d + 255) / 256, nb);
+  MMDIT_CARVEOUT(fold_batch_partials_kernel);
   fold_batch_partials_kernel<<<g2, 256, 0, (cudaStream_t)stream>>>(workspace, dshift, dscale, d, bpb,
                                                                   ld_dmod, ld_dmod, dmod_bf16, dmod_bf16);
   return check_launch("ln_mod_bwd_kernel", 2);
@@ -455,7 +456,7 @@ int mmdit_gate_bwd(const void* dout, const void* a, const void* gate, void* da, 
   const unsigned grid = (unsigned)(nb * bpb);
   const size_t smem = (size_t)BWD_WARPS * 2 * d * sizeof(float);
   MMDIT_REQUIRE(smem <= 48 * 1024, MMDIT_ERR_UNSUPPORTED, "gate_bwd: d=%d too wide", d);
-  DISPATCH_NC(d, (gate_bwd_kernel<NC><<<grid, BWD_THREADS, smem, (cudaStream_t)stream>>>(
+  DISPATCH_NC(d, MMDIT_CARVEOUT(gate_bwd_kernel<NC>); (gate_bwd_kernel<NC><<<grid, BWD_THREADS, smem, (cudaStream_t)stream>>>(
                      (const bf16*)dout, (const bf16*)a, (const bf16*)gate, (bf16*)da, workspace, d,
                      rows_per_batch, ld_gate, rpb, bpb)));
   dim3 g2((2 * d + 255) / 256, nb);

@@ -51,12 +51,26 @@ def test_struct_layouts_match_the_c_compiler(tmp_path):
                    _lib.AttnArgs.d_o.offset, _lib.AttnArgs.delta.offset]
 
 
+def test_comm_struct_layout_matches_the_c_compiler(tmp_path):
+    from mmdit.comm import CommStruct
+    prog = tmp_path / "sz.cpp"
+    prog.write_text('#include "mmdit_b200.h"\n#include <stdio.h>\n#include <stddef.h>\n'
+                    'int main(){printf("%zu %zu %zu %zu\\n", sizeof(mmdit_comm), offsetof(mmdit_comm, flag),'
+                    'offsetof(mmdit_comm, state), offsetof(mmdit_comm, world));}')
+    exe = tmp_path / "sz"
+    subprocess.run(["g++", "-I", os.path.join(ROOT, "include"), str(prog), "-o", str(exe)], check=True)
+    got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    assert got == [ctypes.sizeof(CommStruct), CommStruct.flag.offset, CommStruct.state.offset,
+                   CommStruct.world.offset]
+
+
 def test_sass_is_blackwell_native():
     """tcgen05 / TMA / TMEM mnemonics must be in the shipped cubin (B200_PROFILING.md)."""
     out = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
     if not out:
         pytest.skip("cuobjdump unavailable")
-    for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM", "STTM"):
+    # UTMASTG: TMA-store epilogues; the CTA-pair GEMM shows as UTCHMMA.2CTA
+    for mnemonic in ("UTCHMMA", "UTMALDG", "UTMASTG", "LDTM", "STTM"):
         assert mnemonic in out, mnemonic
     assert "HMMA." not in out.replace("UTCHMMA", "")  # no legacy mma.sync tensor path
 

@@ -242,25 +242,38 @@ class HostFeed:
         self.stream = torch.cuda.Stream(device=device)
         self.pending = None
 
-    def submit(self, host_batch_):
+    def submit(self, host_batch_, latent_hw=None):
         with torch.cuda.stream(self.stream):
             dev = {k: v.to(self.device, non_blocking=True) for k, v in host_batch_.items()}
             ev = torch.cuda.Event()
             ev.record(self.stream)
-        self.pending = (dev, ev)
+        self.pending = (dev, ev, latent_hw)
+
+    def submit_wire(self, wire, time_sampler=None, p_null=(0.1, 0.316, 0.316)):
+        """Queue a batch in the reference's loader wire format (mmdit/feed.py): the latent shape is
+        inferred on the host, the +inf-padded latents travel as one contiguous copy."""
+        from . import feed
+        hb, hw = feed.from_wire(wire, time_sampler, p_null)
+        self.submit(hb, hw)
 
     def take(self):
-        dev, ev = self.pending
+        dev, ev, hw = self.pending
         torch.cuda.current_stream().wait_event(ev)
         for v in dev.values():
             v.record_stream(torch.cuda.current_stream())
         self.pending = None
+        if hw is not None:
+            from . import feed
+            dev = feed.finish_on_device(dev, hw)     # crop the padded latents (device slice copy)
         return dev
 
 
 class RFTrainer:
     def __init__(self, model, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01, clip=1.0,
-                 world_size=1, process_group=None, use_graph=False, fused_optimizer=True, peer=None):
+                 world_size=1, process_group=None, use_graph=False, fused_optimizer=True, peer=None,
+                 ema=None):
+        """ema: optional mmdit.ema.DeviceEMA, blended in after the optimizer every `update_freq`
+        steps (model_trainer.py:537-541) -- on the device, no D2H copy of the weights."""
         self.model = model
         self.device = next(model.parameters()).device
         self.clip = clip
@@ -279,6 +292,8 @@ class RFTrainer:
         else:
             self.opt = torch.optim.AdamW(self.params, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay,
                                          fused=True, capturable=self.use_graph)
+        self.ema = ema
+        self.steps_done = 0
         self._bound = False
         self.graph = None
         self.graph_opt = None
@@ -334,6 +349,7 @@ class RFTrainer:
             self._zero()
             loss = self._fwd_bwd(batch)
             self._update()
+            self._after_step()
             return loss
         if self.graph is None:
             self._capture(batch)
@@ -345,7 +361,13 @@ class RFTrainer:
             # (capturing NCCL work issued from autograd hooks hung in testing on this stack)
             self.buckets.all_reduce_mean()
             self.graph_opt.replay()
+        self._after_step()
         return self.loss
+
+    def _after_step(self):
+        self.steps_done += 1
+        if self.ema is not None:
+            self.ema.update(self.steps_done)
 
     def _capture(self, batch):
         self.static = {k: v.clone() for k, v in batch.items()}

@@ -77,3 +77,49 @@ def test_two_rank_bucketed_allreduce_matches_full_batch():
         assert keys == [("block", 2), ("block", 1), ("block", 0), ("rest", 0)]
         assert order[-4:] == [("rest", 0), ("block", 2), ("block", 1), ("block", 0)] or \
             order[-4:] == [("block", 2), ("block", 1), ("block", 0), ("rest", 0)] or len(order) >= 4
+
+
+def test_bucket_slots_are_aligned_and_packed_groups_are_adjacent():
+    """Host logic of the direct-to-bucket weight gradients (no process group needed): every slot
+    starts on a 64-byte boundary, the parameters of one packed GEMM (`adjacent` hint) sit back to
+    back in the hinted order, and functional._wgrad_slot only aliases slots that really are."""
+    sys.path.insert(0, os.path.join(ROOT, "stable-diffusion-3-from-scratch_b200"))
+    from mmdit.functional import _wgrad_slot
+    from mmdit.train import GradBuckets
+
+    class Blk(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.s = nn.Parameter(torch.zeros(3))            # odd size: forces padding after it
+            self.q = nn.Linear(16, 16, bias=False)
+            self.b = nn.Parameter(torch.zeros(5))
+            self.k = nn.Linear(16, 16, bias=False)
+            self.v = nn.Linear(16, 16, bias=False)
+
+    class M(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.blocks = nn.ModuleList([Blk(), Blk()])
+            self.head = nn.Linear(16, 4)
+
+    m = M()
+    hint = [[blk.v.weight, blk.q.weight, blk.k.weight] for blk in m.blocks]   # packed order != named order
+    gb = GradBuckets(list(m.named_parameters()), 1, None, torch.device("cpu"), peer=False, adjacent=hint)
+    assert [k for k, _, _ in gb.buckets] == [("block", 1), ("block", 0), ("rest", 0)]
+    for _, flat, ps in gb.buckets:
+        assert {id(p) for p in ps} <= {id(p) for p in m.parameters()}
+        for p in ps:
+            assert p._grad_slot.data_ptr() % 64 == 0 and p._grad_slot.shape == p.shape
+            assert flat.data_ptr() <= p._grad_slot.data_ptr() < flat.data_ptr() + flat.numel() * 4
+    for blk in m.blocks:
+        out = _wgrad_slot([blk.v.weight, blk.q.weight, blk.k.weight])
+        assert out is not None and out.shape == (48, 16)
+        out.fill_(0.0)
+        out[16:32].fill_(2.0)                                   # rows of the 2nd packed parameter
+        assert float(blk.q.weight._grad_slot.sum()) == 2.0 * 256 and float(blk.v.weight._grad_slot.sum()) == 0.0
+        assert _wgrad_slot([blk.q.weight, blk.v.weight]) is None   # not adjacent in this order
+    assert _wgrad_slot([nn.Parameter(torch.zeros(4, 4))]) is None  # no slot at all
+    # a step without any backward: every slot reads zero, .grad is the slot
+    gb.reset()
+    gb.all_reduce_mean()
+    assert all(p.grad is p._grad_slot and float(p.grad.abs().sum()) == 0.0 for p in m.parameters())

@@ -43,10 +43,14 @@ def host_batch(B, C, h, w, M=154, class_dim=768, seed=0, p_null=(0.1, 0.316, 0.3
 
 
 class GradBuckets:
-    """Flat fp32 gradient buckets for data-parallel all-reduce (replaces the DDP reducer,
-    model_trainer.py:224).  One bucket per transformer block plus one for everything else;
-    param.grad tensors are views into the flat buffers, so the reduce needs no copies
-    (torch DDP's default copies every gradient into its buckets: an extra 4*P-byte pass)."""
+    """Flat fp32 gradient buckets for the data-parallel exchange (replaces the DDP reducer,
+    model_trainer.py:224).  One bucket per transformer block plus one for everything else.  Every
+    parameter owns a 64-byte aligned slot (`p._grad_slot`) inside its bucket; at the start of a
+    step `.grad` is dropped, the packed wgrad GEMMs write their slots directly, any other fresh
+    gradient is copied into its slot by the post-accumulate hook, and `.grad` then IS the slot --
+    no zero-fill and no accumulate pass over the buckets (torch DDP's default copies every gradient
+    into its buckets: an extra 4*P-byte pass).  On CUDA the buckets live in one IPC-exported arena
+    (mmdit/comm.py) and are reduced by our peer-memory kernel; otherwise by dist.all_reduce."""
 
     def __init__(self, named_params, world_size, process_group=None, device=None, peer=None, adjacent=()):
         """adjacent: lists of parameters that one packed GEMM produces the gradients of (e.g. the

@@ -13,6 +13,8 @@
 //   3. the last CTA to finish tells every peer "my shard is written" and waits for all peers.
 // Flags carry a device-resident epoch (advanced by the kernel itself), so the same captured
 // launch can be replayed forever.  All spins are bounded (trap instead of hanging the GPU).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "mmdit_b200.h"
 
@@ -60,7 +62,11 @@ __device__ __forceinline__ void spin_until(const uint32_t* p, uint32_t target) {
   }
 }
 
-template <int W>
+// U: batches of W peer loads issued before the first use (U x W x 16 bytes in flight per thread).
+// Default U = 8 / W (8 loads in flight); MMDIT_COMM_UNROLL=2|4 multiplies it (W = 8: the
+// 16-byte peer loads reached only 19 % of the NVLink rate on a 24 MB bucket -- more bytes in
+// flight per thread is the first thing to sweep).
+template <int W, int U>
 __global__ void __launch_bounds__(COMM_THREADS) allreduce_mean_kernel(const CommParams p) {
   __shared__ uint32_t s_epoch;
   if (threadIdx.x == 0) s_epoch = *reinterpret_cast<volatile uint32_t*>(p.state);
@@ -74,7 +80,6 @@ __global__ void __launch_bounds__(COMM_THREADS) allreduce_mean_kernel(const Comm
 
   // 2. reduce-scatter + all-gather of this rank's shard, 16 bytes per thread and peer;
   //    U x W = 8 peer loads in flight per thread whatever the world size
-  constexpr int U = W >= 8 ? 1 : 8 / W;
   const long long n4 = p.n >> 2;
   const long long per = (n4 + W - 1) / W;
   const long long lo = p.rank * per, hi = min(n4, lo + per);
@@ -206,14 +211,33 @@ extern "C" int mmdit_allreduce_mean_f32(const mmdit_comm* c, int64_t offset, int
   p.scale = 1.0f / (float)c->world;
   if (ctas <= 0) ctas = 48;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  static int mult = -1;
+  if (mult < 0) {
+    const char* e = getenv("MMDIT_COMM_UNROLL");
+    mult = e ? atoi(e) : 1;
+    if (mult != 2 && mult != 4) mult = 1;
+  }
+#define COMM_LAUNCH(WW, UU)                                            \
+  do {                                                                 \
+    MMDIT_CARVEOUT((allreduce_mean_kernel<WW, UU>));                   \
+    allreduce_mean_kernel<WW, UU><<<ctas, COMM_THREADS, 0, s>>>(p);    \
+  } while (0)
+#define COMM_CASE(WW, U1)                                              \
+  case WW:                                                             \
+    if (mult == 4) COMM_LAUNCH(WW, 4 * U1);                            \
+    else if (mult == 2) COMM_LAUNCH(WW, 2 * U1);                       \
+    else COMM_LAUNCH(WW, U1);                                          \
+    break;
   switch (c->world) {
-    case 1: MMDIT_CARVEOUT(allreduce_mean_kernel<1>); allreduce_mean_kernel<1><<<ctas, COMM_THREADS, 0, s>>>(p); break;
-    case 2: MMDIT_CARVEOUT(allreduce_mean_kernel<2>); allreduce_mean_kernel<2><<<ctas, COMM_THREADS, 0, s>>>(p); break;
-    case 4: MMDIT_CARVEOUT(allreduce_mean_kernel<4>); allreduce_mean_kernel<4><<<ctas, COMM_THREADS, 0, s>>>(p); break;
-    case 8: MMDIT_CARVEOUT(allreduce_mean_kernel<8>); allreduce_mean_kernel<8><<<ctas, COMM_THREADS, 0, s>>>(p); break;
+    COMM_CASE(1, 8)
+    COMM_CASE(2, 4)
+    COMM_CASE(4, 2)
+    COMM_CASE(8, 1)
     default:
       set_last_error("allreduce: world size %d not supported (1, 2, 4, 8)", c->world);
       return MMDIT_ERR_UNSUPPORTED;
   }
+#undef COMM_CASE
+#undef COMM_LAUNCH
   return check_launch("allreduce_mean_kernel");
 }

@@ -32,8 +32,23 @@ def side(device):
     return s
 
 
+# Under no_grad (sampling) nothing is saved for a backward, so a tensor that crosses the streams
+# could be freed -- and recycled by the caching allocator on its home stream -- while the other
+# stream still reads it.  With MMDIT_DUAL_STREAM_INFER=1 the blocks park those tensors in
+# `infer_keepalive` until the end-of-forward join (diff_model.forward clears it).  Off by default:
+# not yet timed / validated on hardware.
+INFER = os.environ.get("MMDIT_DUAL_STREAM_INFER", "0") == "1"
+infer_keepalive = []
+
+
 def active(t):
-    return ENABLED and t.is_cuda and torch.is_grad_enabled()
+    return ENABLED and t.is_cuda and (torch.is_grad_enabled() or INFER)
+
+
+def hold(*tensors):
+    """Keep tensors that cross the streams alive until the forward's final join (no_grad only)."""
+    if not torch.is_grad_enabled():
+        infer_keepalive.extend(tensors)
 
 
 # ---- weight gradients off the critical path ------------------------------------------------

@@ -144,10 +144,12 @@ class Transformer_Block_Dual(nn.Module):
         qkv_x = self.attn.project_qkv(xn, "x")
         main.wait_stream(side)                      # text q|k|v ready
         a_x, a_c = self.attn.attend_qkv(qkv_x, qkv_c, orig_shape, B, N, M)
+        streams.hold(*m, qkv_c, a_c, c)             # no_grad only: tensors both streams touch
         if not self.last:
             side.wait_stream(main)                  # attention output ready
             with torch.cuda.stream(side):
                 c = self._c_branch(a_c, c, m, B, M)
+                streams.hold(c)
         X = self._x_branch(a_x, X, m, B, N)
         if self.last:
             main.wait_stream(side)                  # nothing of the text branch is left in flight

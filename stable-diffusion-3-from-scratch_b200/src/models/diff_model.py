@@ -177,6 +177,7 @@ class diff_model(nn.Module):
             x, cseq = block(x, cseq, y, orig_shape, yp=yp)
         if streams.active(x):   # two-stream block schedule: the text branch must not outlive the forward
             torch.cuda.current_stream().wait_stream(streams.side(x.device))
+            streams.infer_keepalive.clear()
 
         # output head (:339,342)
         x = self._linear(self.out_proj, self.out_norm(x, y))

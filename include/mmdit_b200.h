@@ -54,8 +54,11 @@ enum {
   MMDIT_EPI_GATE_RESID = 1,/* D = (acc+bias) * gate[m/rows_per_gate, n] + resid */
   MMDIT_EPI_SILU = 2,      /* D = silu(acc+bias)                                */
   MMDIT_EPI_RESID = 3,     /* D = acc + bias + resid                            */
-  MMDIT_EPI_SWIGLU = 4     /* B = [gate rows; up rows] (xformers w12, MLP.py:19): D[M,N/2] = silu(g)*u,
+  MMDIT_EPI_SWIGLU = 4,    /* B = [gate rows; up rows] (xformers w12, MLP.py:19): D[M,N/2] = silu(g)*u,
                               aux[M,N] = acc+bias (bf16, required); needs N % 256 == 0, M > 128 */
+  MMDIT_EPI_QKNORM = 5     /* B = [q; k; v] rows (N = 3d): D[M,N] = acc (+bias), aux[M,2d] = per-head
+                              RMSNorm * weight (+ 2-D RoPE) of the q and k columns (Attention.py:61-64,
+                              130-134,174-194); experimental, not yet validated on hardware */
 };
 
 typedef struct mmdit_gemm_args {
@@ -84,6 +87,13 @@ typedef struct mmdit_gemm_args {
   int64_t remap_rows, remap_batch_rows, remap_offset;
   int32_t force_block_n; /* 0 = auto; else 64/128/256 (testing) */
   int32_t reserved;
+  /* MMDIT_EPI_QKNORM only */
+  const void* qk_wq;     /* fp32 [64] */
+  const void* qk_wk;     /* fp32 [64] */
+  const void* rope_cos;  /* fp32 [tokens, 32] or NULL (no rotation: text stream) */
+  const void* rope_sin;
+  int32_t qk_tokens;     /* tokens per sample: position of row m is m % qk_tokens */
+  float qk_eps;
 } mmdit_gemm_args;
 
 int mmdit_gemm_bf16(const mmdit_gemm_args* args, void* stream);

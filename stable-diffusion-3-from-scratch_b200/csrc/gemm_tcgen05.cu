@@ -54,6 +54,14 @@ struct GemmParams {
   long long remap_rows, remap_batch_rows, remap_offset;
   long long slice_stride;  // split-K slices mode: split ks writes D + ks*slice_stride (no atomics)
   int debug;  // bit0: skip global stores, bit1: skip TMEM loads (perf experiments only)
+  // EV_QKNORM_TMA (appended: the offsets of everything above stay what the other variants use)
+  const float* qk_wq;      // [64] RMSNorm weight of q
+  const float* qk_wk;      // [64] RMSNorm weight of k
+  const float* rope_cos;   // [tokens, 32] or null (text stream)
+  const float* rope_sin;
+  int qk_d;                // model width: columns [0,d) = q, [d,2d) = k, [2d,3d) = v
+  int qk_tokens;           // tokens per sample (row -> position for RoPE)
+  float qk_eps;
 };
 
 __device__ __forceinline__ float bias_at(const GemmParams& p, int n) {
@@ -139,7 +147,14 @@ __device__ __forceinline__ void epilogue8(const GemmParams& p, long long m, long
 // (all run-time flags resolved at compile time, full 8-column vectors, 16-byte aligned rows);
 // EV_GENERIC keeps every option behind run-time flags (tails, remap, SiLU, odd alignments).
 enum { EV_GENERIC = 0, EV_BF16 = 1, EV_BF16_BIAS = 2, EV_GATE = 3, EV_F32 = 4, EV_F32_ATOMIC = 5,
-       EV_BF16_TMA = 6, EV_SWIGLU_TMA = 7 };
+       EV_BF16_TMA = 6, EV_SWIGLU_TMA = 7, EV_QKNORM_TMA = 8 };
+// EV_QKNORM_TMA (experimental, MMDIT_FUSED_QKNORM=1; NOT yet validated on hardware): the packed
+// q|k|v projection writes the raw projection (D, needed by the backward) and, for the q and k
+// columns, the per-head RMSNorm * weight followed by the 2-D RoPE rotation (aux = [M, 2d]) --
+// Attention.py:61-64,130-134,174-194 in the producer's epilogue.  A 64-column chunk is exactly one
+// head and the epilogue thread owns the whole row of it, so the norm needs no shuffles; the
+// arithmetic (bf16-rounded projection in, fp32 norm, bf16 rounding before the rotation, summation
+// order of the squares) restates qknorm_rope_fwd_kernel so that both paths agree bit for bit.
 // EV_SWIGLU_TMA (CTA pairs only): B = xformers' w12 ([gate rows; up rows], MLP.py:19).  The leader
 // CTA stages 128 gate rows, its peer the matching 128 up rows, so every accumulator row holds
 // gate[128] | up[128] of the same hidden columns: the epilogue writes the pre-activation (aux,
@@ -409,7 +424,100 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
       float* wbuf = reinterpret_cast<float*>(stage_buf + ew * (32 * 64 * 4));
       const int nchunks = block_n / 64;
       const int sub_row = lane >> 3, seg = lane & 7;
-      if constexpr (EV == EV_SWIGLU_TMA) {
+      if constexpr (EV == EV_QKNORM_TMA) {
+        uint8_t* sbase = stage_buf + ew * (32 * 64 * 4);
+        const float* bp = reinterpret_cast<const float*>(p.bias);
+        auto stage_tile = [&](const uint32_t (&packed)[32], const CUtensorMap* tm, int col) {
+          uint8_t* tile = sbase + (tma_buf & 1) * 4096;
+          if (lane == 0) tma_wait_group_read1();
+          __syncwarp();
+          uint8_t* prow = tile + lane * 128;
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<uint4*>(prow + ((j ^ (lane & 7)) << 4)) =
+                make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0 && !(p.debug & 1)) {
+            tma_store_2d(tm, tile, col, static_cast<int>(m0));
+            tma_commit_group();
+          }
+          ++tma_buf;
+        };
+        const int nchunks_q = block_n / 64;
+        for (int c = 0; c < nchunks_q; ++c) {
+          const int n = n_blk * block_n + c * 64;
+          uint32_t pk[32];
+          {
+            uint32_t r0[32], r1[32];
+            tmem_ld32(taddr + c * 64, r0);
+            tmem_ld32(taddr + c * 64 + 32, r1);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const uint32_t* src = j < 8 ? &r0[4 * j] : &r1[4 * (j - 8)];
+              float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (bp && n + 4 * j < p.N) b = __ldg(reinterpret_cast<const float4*>(bp + n + 4 * j));
+              pk[2 * j] = pack_bf16x2(__uint_as_float(src[0]) + b.x, __uint_as_float(src[1]) + b.y);
+              pk[2 * j + 1] = pack_bf16x2(__uint_as_float(src[2]) + b.z, __uint_as_float(src[3]) + b.w);
+            }
+          }
+          if (c == nchunks_q - 1) {  // accumulator drained: hand the TMEM stage back
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              if constexpr (PAIR) mbar_arrive_cluster(leader_tmem_empty + as * 8);
+              else mbar_arrive(&tmem_empty[as]);
+            }
+          }
+          if (n >= p.N || m0 >= p.M) continue;
+          stage_tile(pk, &p.tmD, n);                 // raw projection (bf16), all of q | k | v
+          const int part = n / p.qk_d;               // 0: q, 1: k, 2: v
+          if (part >= 2) continue;
+          const float* w = part == 0 ? p.qk_wq : p.qk_wk;
+          // sum of squares: 8 sequential partial sums of 8, combined as the 8-lane xor tree of
+          // qknorm_rope_fwd_kernel does ((s0+s1)+(s2+s3)) + ((s4+s5)+(s6+s7))
+          float sg[8];
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            float a = 0.f;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float2 v = unpack_bf16x2(pk[4 * g + j]);
+              a += v.x * v.x;
+              a += v.y * v.y;
+            }
+            sg[g] = a;
+          }
+          const float ss = ((sg[0] + sg[1]) + (sg[2] + sg[3])) + ((sg[4] + sg[5]) + (sg[6] + sg[7]));
+          const float rn = rsqrtf(ss * (1.f / 64.f) + p.qk_eps);
+          const long long mrow = m0 + lane;
+          const int tok = static_cast<int>(static_cast<unsigned long long>(mrow) %
+                                           static_cast<unsigned>(p.qk_tokens > 0 ? p.qk_tokens : 1));
+          const float* cs = p.rope_cos ? p.rope_cos + static_cast<long long>(tok) * 32 : nullptr;
+          const float* sn = p.rope_sin ? p.rope_sin + static_cast<long long>(tok) * 32 : nullptr;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {   // 4 columns = 2 rotation pairs per trip
+            const float4 wv = __ldg(reinterpret_cast<const float4*>(w + 4 * j));
+            const float2 a = unpack_bf16x2(pk[2 * j]), b = unpack_bf16x2(pk[2 * j + 1]);
+            // the reference rounds the RMSNorm output to bf16 before the fp32 rotation
+            float y0 = __bfloat162float(__float2bfloat16(a.x * rn * wv.x));
+            float y1 = __bfloat162float(__float2bfloat16(a.y * rn * wv.y));
+            float y2 = __bfloat162float(__float2bfloat16(b.x * rn * wv.z));
+            float y3 = __bfloat162float(__float2bfloat16(b.y * rn * wv.w));
+            if (cs) {
+              const float2 cc = *reinterpret_cast<const float2*>(cs + 2 * j);
+              const float2 sv = *reinterpret_cast<const float2*>(sn + 2 * j);
+              const float t0 = y0 * cc.x - y1 * sv.x, t1 = y1 * cc.x + y0 * sv.x;
+              const float t2 = y2 * cc.y - y3 * sv.y, t3 = y3 * cc.y + y2 * sv.y;
+              y0 = t0; y1 = t1; y2 = t2; y3 = t3;
+            }
+            pk[2 * j] = pack_bf16x2(y0, y1);
+            pk[2 * j + 1] = pack_bf16x2(y2, y3);
+          }
+          stage_tile(pk, &p.tmAux, n);               // aux is [M, 2d]: q at column 0, k at column d
+        }
+      } else if constexpr (EV == EV_SWIGLU_TMA) {
         uint8_t* sbase = stage_buf + ew * (32 * 64 * 4);
         const float* bp = reinterpret_cast<const float*>(p.bias);
         auto stage_tile = [&](const uint32_t (&packed)[32], const CUtensorMap* tm, int col) {
@@ -580,7 +688,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
       as ^= 1;
       if (as == 0) aphase ^= 1;
     }
-    if constexpr (EV == EV_BF16_TMA || EV == EV_SWIGLU_TMA) {
+    if constexpr (EV == EV_BF16_TMA || EV == EV_SWIGLU_TMA || EV == EV_QKNORM_TMA) {
       if (lane == 0) tma_wait_group0();  // staging tiles must outlive their stores
     }
   }
@@ -665,7 +773,7 @@ extern "C" int mmdit_gemm_bf16(const mmdit_gemm_args* a, void* stream_) {
   MMDIT_REQUIRE(!(a->accumulate && !a->d_fp32), MMDIT_ERR_ARG, "gemm: accumulate needs fp32 D");
   MMDIT_REQUIRE(a->epilogue == MMDIT_EPI_NONE || a->epilogue == MMDIT_EPI_GATE_RESID ||
                     a->epilogue == MMDIT_EPI_SILU || a->epilogue == MMDIT_EPI_RESID ||
-                    a->epilogue == MMDIT_EPI_SWIGLU,
+                    a->epilogue == MMDIT_EPI_SWIGLU || a->epilogue == MMDIT_EPI_QKNORM,
                 MMDIT_ERR_UNSUPPORTED, "gemm: epilogue %d not supported", a->epilogue);
   if (a->epilogue == MMDIT_EPI_GATE_RESID)
     MMDIT_REQUIRE(a->gate && a->rows_per_gate > 0 && a->resid, MMDIT_ERR_ARG,
@@ -683,6 +791,18 @@ extern "C" int mmdit_gemm_bf16(const mmdit_gemm_args* a, void* stream_) {
                   "gemm: the SwiGLU epilogue needs aux, bf16 D [M,N/2], K-major B, N %% 256 == 0, M > 128, "
                   "16-byte aligned rows and an fp32 bias");
   }
+  const bool qknorm = a->epilogue == MMDIT_EPI_QKNORM;
+  if (qknorm) {
+    auto al = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+    MMDIT_REQUIRE(a->aux && a->qk_wq && a->qk_wk && !a->d_fp32 && !a->accumulate && a->split_k <= 1 &&
+                      a->remap_rows == 0 && a->N % 192 == 0 && a->M > BLOCK_M && al(a->D) && al(a->aux) &&
+                      al(a->qk_wq) && al(a->qk_wk) && a->ldd % 8 == 0 && a->ld_aux % 8 == 0 &&
+                      (!a->bias || (a->bias_fp32 && al(a->bias))) && (!a->rope_cos == !a->rope_sin) &&
+                      (!a->rope_cos || (a->qk_tokens > 0 && al(a->rope_cos) && al(a->rope_sin))),
+                  MMDIT_ERR_UNSUPPORTED,
+                  "gemm: the QK-norm epilogue needs aux [M, 2N/3], bf16 D, N = 3*d with d %% 64 == 0, M > 128, "
+                  "fp32 16-byte aligned norm weights / RoPE tables");
+  }
   const int sms = num_sms();
   GemmParams p;
   memset(&p, 0, sizeof(p));
@@ -692,7 +812,7 @@ extern "C" int mmdit_gemm_bf16(const mmdit_gemm_args* a, void* stream_) {
   // split-K GEMMs (explicit slices / fp32 accumulate) fill the machine through the split, not through
   // narrower tiles: the split planners (here and ops._plan_split) assume 128x256 tiles
   const bool will_split = a->split_k > 1 || (a->split_k <= 0 && a->accumulate && a->d_fp32 && a->K >= 8 * BLOCK_K);
-  p.block_n = swiglu ? 256 : a->force_block_n ? a->force_block_n
+  p.block_n = (swiglu || qknorm) ? 256 : a->force_block_n ? a->force_block_n
               : (will_split && a->N > 128) ? 256 : pick_block_n(a->M, a->N, sms);
   MMDIT_REQUIRE(p.block_n == 64 || p.block_n == 128 || p.block_n == 256, MMDIT_ERR_ARG,
                 "gemm: block_n %d", p.block_n);
@@ -702,7 +822,7 @@ extern "C" int mmdit_gemm_bf16(const mmdit_gemm_args* a, void* stream_) {
     const char* e = getenv("MMDIT_GEMM_PAIR");
     env_pair = e ? atoi(e) : 1;
   }
-  const bool pair = swiglu || (env_pair && p.block_n == 256 && a->M > BLOCK_M && !(a->reserved & 16));
+  const bool pair = swiglu || qknorm || (env_pair && p.block_n == 256 && a->M > BLOCK_M && !(a->reserved & 16));
   const int workers = pair ? sms / 2 : sms;  // persistent work units running concurrently
   const int stage_bytes = A_STAGE_BYTES + (pair ? p.block_n / 2 : p.block_n) * BLOCK_K * 2;
   p.stages = (SMEM_BUDGET - 1024 - BAR_BYTES - EPI_STAGE_BYTES) / stage_bytes;
@@ -787,6 +907,15 @@ extern "C" int mmdit_gemm_bf16(const mmdit_gemm_args* a, void* stream_) {
   int ev = EV_GENERIC;
   if (swiglu) {
     ev = EV_SWIGLU_TMA;
+  } else if (qknorm) {
+    ev = EV_QKNORM_TMA;
+    p.qk_wq = static_cast<const float*>(a->qk_wq);
+    p.qk_wk = static_cast<const float*>(a->qk_wk);
+    p.rope_cos = static_cast<const float*>(a->rope_cos);
+    p.rope_sin = static_cast<const float*>(a->rope_sin);
+    p.qk_d = (int)(a->N / 3);
+    p.qk_tokens = a->qk_tokens;
+    p.qk_eps = a->qk_eps;
   } else if (vec_ok) {
     if (a->d_fp32) {
       if (a->epilogue == MMDIT_EPI_NONE && !a->bias && !a->aux) {
@@ -810,13 +939,13 @@ extern "C" int mmdit_gemm_bf16(const mmdit_gemm_args* a, void* stream_) {
   }
   MMDIT_REQUIRE(p.slice_stride == 0 || ev == EV_F32, MMDIT_ERR_ALIGN,
                 "gemm: split-K slices mode needs N %% 8 == 0 and 16-byte aligned D");
-  if (ev == EV_BF16_TMA || ev == EV_SWIGLU_TMA) {
+  if (ev == EV_BF16_TMA || ev == EV_SWIGLU_TMA || ev == EV_QKNORM_TMA) {
     uint64_t dims[2] = {(uint64_t)(swiglu ? a->N / 2 : a->N), (uint64_t)a->M}, strides[1] = {(uint64_t)a->ldd * 2};
     uint32_t box[2] = {64, 32};
     int rc_d = encode_tmap(&p.tmD, a->D, 2, dims, strides, box, 2, true);
     if (rc_d) return rc_d;
-    if (swiglu) {
-      dims[0] = (uint64_t)a->N;
+    if (swiglu || qknorm) {
+      dims[0] = (uint64_t)(qknorm ? a->N / 3 * 2 : a->N);
       strides[0] = (uint64_t)a->ld_aux * 2;
       rc_d = encode_tmap(&p.tmAux, a->aux, 2, dims, strides, box, 2, true);
       if (rc_d) return rc_d;
@@ -838,6 +967,9 @@ extern "C" int mmdit_gemm_bf16(const mmdit_gemm_args* a, void* stream_) {
     LAUNCH_EV(EV_BF16_TMA)
     case EV_SWIGLU_TMA:
       rc = launch_variant<EV_SWIGLU_TMA, true>(grid, smem_bytes, stream, p);
+      break;
+    case EV_QKNORM_TMA:
+      rc = launch_variant<EV_QKNORM_TMA, true>(grid, smem_bytes, stream, p);
       break;
   }
 #undef LAUNCH_EV

@@ -31,6 +31,8 @@ class GemmArgs(C.Structure):
         ("aux", c_vp), ("ld_aux", c_i64),
         ("remap_rows", c_i64), ("remap_batch_rows", c_i64), ("remap_offset", c_i64),
         ("force_block_n", c_i32), ("reserved", c_i32),
+        ("qk_wq", c_vp), ("qk_wk", c_vp), ("rope_cos", c_vp), ("rope_sin", c_vp),
+        ("qk_tokens", c_i32), ("qk_eps", c_f32),
     ]
 
 
@@ -52,7 +54,7 @@ class AttnArgs(C.Structure):
     ]
 
 
-EPI_NONE, EPI_GATE_RESID, EPI_SILU, EPI_RESID, EPI_SWIGLU = 0, 1, 2, 3, 4
+EPI_NONE, EPI_GATE_RESID, EPI_SILU, EPI_RESID, EPI_SWIGLU, EPI_QKNORM = 0, 1, 2, 3, 4, 5
 
 _lib = None
 

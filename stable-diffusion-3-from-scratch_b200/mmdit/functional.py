@@ -20,6 +20,9 @@ from .ops import BF16, F32
 FUSED_GATE_EPILOGUE = os.environ.get("MMDIT_FUSED_GATE", "0") == "1"
 # MMDIT_FUSED_SWIGLU=0 keeps silu(x1)*x2 in its own kernel instead of the w12 GEMM's epilogue
 FUSED_SWIGLU = os.environ.get("MMDIT_FUSED_SWIGLU", "1") == "1"
+# MMDIT_FUSED_QKNORM=1 (experimental, not yet validated on hardware): per-head RMSNorm + 2-D RoPE of
+# q and k in the epilogue of the packed q|k|v projection (QKVProjFn / JointAttentionPreNormFn below)
+FUSED_QKNORM = os.environ.get("MMDIT_FUSED_QKNORM", "0") == "1"
 
 
 def _wgrad_slot(params):
@@ -238,6 +241,64 @@ class JointAttentionFn(Function):
         ops.qknorm_rope_bwd(dqk_x, qkv_x, wq_x, wk_x, rope, dqkv_x, dw[0], dw[1], d, N)
         ops.qknorm_rope_bwd(dqk_c, qkv_c, wq_c, wk_c, None, dqkv_c, dw[2], dw[3], d, M)
         return dqkv_x, dqkv_c, dw[0], dw[1], dw[2], dw[3], None, None, None, None, None, None
+
+
+class QKVProjFn(Function):
+    """Packed q|k|v projection (Attention.py:130-135) whose GEMM epilogue also emits the per-head
+    RMSNorm * weight (+ 2-D RoPE on image tokens) of q and k (Attention.py:61-64,174-194).
+    Returns (qkv raw [R,3d], qk normalised [R,2d]); qk is a non-differentiable side output --
+    JointAttentionPreNormFn owns the backward of norm + RoPE and returns d(raw qkv)."""
+
+    @staticmethod
+    def forward(ctx, x, wb, wq, wk, cos, sin, tokens, *params):
+        x2 = x.reshape(-1, x.shape[-1])
+        d = wb.shape[0] // 3
+        qk = torch.empty((x2.shape[0], 2 * d), device=x.device, dtype=BF16)
+        qkv = ops.gemm(x2, wb, epilogue=ops.EPI_QKNORM, aux=qk,
+                       qknorm=(wq.detach(), wk.detach(), cos, sin, tokens))
+        ctx.save_for_backward(x2, wb)
+        ctx.xshape = x.shape
+        ctx.wparams = params
+        ctx.mark_non_differentiable(qk)
+        return qkv, qk
+
+    @staticmethod
+    def backward(ctx, dqkv, _dqk):
+        x2, wb = ctx.saved_tensors
+        dy2 = dqkv.reshape(-1, dqkv.shape[-1])
+        if not dy2.is_contiguous():
+            dy2 = dy2.contiguous()
+        dx = ops.gemm(dy2, wb, b_major=1).reshape(ctx.xshape) if ctx.needs_input_grad[0] else None
+        dw = _wgrad_gemm(dy2, x2, ctx.wparams)
+        sizes = [p.shape[0] for p in ctx.wparams]
+        grads = [g.view(p.shape) for g, p in zip(_split_rows(dw, sizes), ctx.wparams)]
+        return (dx, None, None, None, None, None, None, *grads)
+
+
+class JointAttentionPreNormFn(Function):
+    """JointAttentionFn for projections that already carry their normalised / rotated q, k
+    (QKVProjFn): same attention, same backward (which recomputes the norm from the raw qkv)."""
+
+    @staticmethod
+    def forward(ctx, qkv_x, qkv_c, qk_x, qk_c, wq_x, wk_x, wq_c, wk_c, rope_cos, rope_sin, Bn, H, N, M):
+        d = H * 64
+        q = (qk_x[:, :d], qk_c[:, :d])
+        k = (qk_x[:, d:], qk_c[:, d:])
+        v = (qkv_x[:, 2 * d:], qkv_c[:, 2 * d:])
+        bound = ops.qk_logit_bound(wq_x, wk_x, wq_c, wk_c, 0.125)
+        o_x, o_c, lse = ops.attn_fwd(q, k, v, Bn, H, N, M, 0.125, logit_bound=bound)
+        ctx.save_for_backward(qkv_x, qkv_c, qk_x, qk_c, o_x, o_c, lse, wq_x, wk_x, wq_c, wk_c,
+                              rope_cos, rope_sin)
+        ctx.dims = (Bn, H, N, M)
+        ctx.set_materialize_grads(False)
+        return o_x, o_c
+
+    @staticmethod
+    def backward(ctx, do_x, do_c):
+        grads = JointAttentionFn.backward(ctx, do_x, do_c)
+        # JointAttentionFn: (dqkv_x, dqkv_c, dwq_x, dwk_x, dwq_c, dwk_c, 6 x None)
+        return (grads[0], grads[1], None, None, grads[2], grads[3], grads[4], grads[5],
+                None, None, None, None, None, None)
 
 
 class SwiGLUFn(Function):

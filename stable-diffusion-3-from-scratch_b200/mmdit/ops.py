@@ -10,7 +10,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import EPI_GATE_RESID, EPI_NONE, EPI_RESID, EPI_SILU, EPI_SWIGLU  # noqa: F401
+from ._lib import EPI_GATE_RESID, EPI_NONE, EPI_QKNORM, EPI_RESID, EPI_SILU, EPI_SWIGLU  # noqa: F401
 
 BF16 = torch.bfloat16
 F32 = torch.float32
@@ -69,7 +69,7 @@ def gemm(A, B, **kw):
 
 def _gemm(A, B, *, a_major=0, b_major=0, out=None, out_dtype=BF16, accumulate=False, split_k=0,
           epilogue=EPI_NONE, bias=None, gate=None, rows_per_gate=0, resid=None, aux=None,
-          remap=None, out_rows=None, force_block_n=0, simt=False, _logical_m=None):
+          remap=None, out_rows=None, force_block_n=0, simt=False, _logical_m=None, qknorm=None):
     """Body of gemm(); the split-K plans below recurse into _gemm so that a wrapper installed on
     ops.gemm (bench.py's per-launch timers) sees every logical GEMM exactly once."""
     _need_cuda(A, B)
@@ -137,6 +137,16 @@ def _gemm(A, B, *, a_major=0, b_major=0, out=None, out_dtype=BF16, accumulate=Fa
     if remap is not None:
         a.remap_rows, a.remap_batch_rows, a.remap_offset = (int(x) for x in remap)
     a.force_block_n = int(force_block_n)
+    if epilogue == EPI_QKNORM:
+        # qknorm = (wq fp32[64], wk fp32[64], rope_cos | None, rope_sin | None, tokens per sample);
+        # aux receives the normalised / rotated q | k ([M, 2N/3])
+        if qknorm is None or aux is None:
+            raise ValueError("gemm: the QK-norm epilogue needs qknorm=(wq, wk, cos, sin, tokens) and aux")
+        wq_, wk_, cos_, sin_, tokens_ = qknorm
+        a.qk_wq, a.qk_wk = wq_.data_ptr(), wk_.data_ptr()
+        a.rope_cos = cos_.data_ptr() if cos_ is not None else None
+        a.rope_sin = sin_.data_ptr() if sin_ is not None else None
+        a.qk_tokens, a.qk_eps = int(tokens_), RMS_EPS
     L = _lib.lib()
     fn = L.mmdit_gemm_bf16_simt if simt else L.mmdit_gemm_bf16
     _lib.check(fn(C.byref(a), _s()), "mmdit_gemm_bf16")

@@ -82,6 +82,35 @@ class Attention(nn.Module):
             ws = [self.query_proj_c.weight, self.key_proj_c.weight, self.value_proj_c.weight]
         return LinearFn.apply(t.reshape(B * T, d), packed_weight(self, "qkv_" + which, ws), None, 0, 3, *ws)
 
+    def project_qkv_prenorm(self, t, which, orig_shape):
+        """Experimental (functional.FUSED_QKNORM): the projection GEMM's epilogue also produces the
+        normalised / rotated q, k.  Returns (qkv [B*T,3d], qk [B*T,2d])."""
+        from mmdit.functional import QKVProjFn
+        B, T, d = t.shape
+        t = t if t.dtype == BF16 else t.to(BF16)
+        cos = sin = None
+        if which == "x":
+            ws = [self.query_proj_x.weight, self.key_proj_x.weight, self.value_proj_x.weight]
+            wq, wk = self.q_norm_x.weight, self.k_norm_x.weight
+            if self.positional_encoding == "RoPE2d":
+                cos, sin = self.rotary_emb.tables(orig_shape[-2] // 2, orig_shape[-1] // 2)
+        else:
+            ws = [self.query_proj_c.weight, self.key_proj_c.weight, self.value_proj_c.weight]
+            wq, wk = self.q_norm_c.weight, self.k_norm_c.weight
+        return QKVProjFn.apply(t.reshape(B * T, d), packed_weight(self, "qkv_" + which, ws), wq, wk,
+                               cos, sin, T, *ws)
+
+    def attend_prenorm(self, x_pair, c_pair, orig_shape, B, N, M):
+        """Joint attention on (qkv, qk) pairs from project_qkv_prenorm."""
+        from mmdit.functional import JointAttentionPreNormFn
+        cos = sin = None
+        if self.positional_encoding == "RoPE2d":
+            cos, sin = self.rotary_emb.tables(orig_shape[-2] // 2, orig_shape[-1] // 2)
+        return JointAttentionPreNormFn.apply(x_pair[0], c_pair[0], x_pair[1], c_pair[1],
+                                             self.q_norm_x.weight, self.k_norm_x.weight,
+                                             self.q_norm_c.weight, self.k_norm_c.weight, cos, sin,
+                                             B, self.num_heads, N, M)
+
     def attend_qkv(self, qkv_x, qkv_c, orig_shape, B, N, M):
         """QK-norm + RoPE + joint attention on the packed projections of both streams."""
         cos = sin = None

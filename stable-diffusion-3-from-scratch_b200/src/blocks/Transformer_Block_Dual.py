@@ -13,7 +13,7 @@ import torch
 from torch import nn
 
 from mmdit import ops, streams
-from mmdit.functional import GatedLinearFn, LinearFn
+from mmdit.functional import FUSED_QKNORM, GatedLinearFn, LinearFn
 from mmdit.shadow import packed_weight
 from src.blocks.Attention import Attention
 from src.blocks.MLP import MLP, SwiGLU
@@ -139,12 +139,20 @@ class Transformer_Block_Dual(nn.Module):
                 cn = modulate(c, m[2], m[3])
             else:
                 cn, c = modulate_keep(c, m[2], m[3])
-            qkv_c = self.attn.project_qkv(cn, "c")
+            fused_qk = FUSED_QKNORM and B * M > 128 and B * N > 128     # experimental, off by default
+            qkv_c = (self.attn.project_qkv_prenorm(cn, "c", orig_shape) if fused_qk
+                     else self.attn.project_qkv(cn, "c"))
         xn, X = modulate_keep(X, m[0], m[1])
-        qkv_x = self.attn.project_qkv(xn, "x")
-        main.wait_stream(side)                      # text q|k|v ready
-        a_x, a_c = self.attn.attend_qkv(qkv_x, qkv_c, orig_shape, B, N, M)
-        streams.hold(*m, qkv_c, a_c, c)             # no_grad only: tensors both streams touch
+        if fused_qk:
+            qkv_x = self.attn.project_qkv_prenorm(xn, "x", orig_shape)
+            main.wait_stream(side)
+            a_x, a_c = self.attn.attend_prenorm(qkv_x, qkv_c, orig_shape, B, N, M)
+            streams.hold(*m, *qkv_c, a_c, c)
+        else:
+            qkv_x = self.attn.project_qkv(xn, "x")
+            main.wait_stream(side)                      # text q|k|v ready
+            a_x, a_c = self.attn.attend_qkv(qkv_x, qkv_c, orig_shape, B, N, M)
+            streams.hold(*m, qkv_c, a_c, c)             # no_grad only: tensors both streams touch
         if not self.last:
             side.wait_stream(main)                  # attention output ready
             with torch.cuda.stream(side):

@@ -201,6 +201,38 @@ def group_swiglu():
     return ok
 
 
+def group_qknorm():
+    """EXPERIMENTAL epilogue (MMDIT_EPI_QKNORM): fused q|k|v projection + per-head RMSNorm + 2-D RoPE
+    == plain GEMM followed by mmdit_qknorm_rope_fwd, bit for bit (image stream with RoPE tables and
+    text stream without)."""
+    sys.path.insert(0, os.path.join(ROOT, "stable-diffusion-3-from-scratch_b200"))
+    from mmdit import ops
+    ok = True
+    for (B, T, d, rope) in [(2, 256, 256, True), (2, 154, 256, False), (64, 256, 768, True), (64, 154, 768, False),
+                            (3, 240, 128, True)]:
+        torch.manual_seed(T + d)
+        R = B * T
+        x = torch.randn(R, d, device=dev).bfloat16()
+        w = (torch.randn(3 * d, d, device=dev) / d ** 0.5).bfloat16()
+        wq = (1 + 0.1 * torch.randn(64, device=dev)).float(); wk = (1 + 0.1 * torch.randn(64, device=dev)).float()
+        tabs = None
+        if rope:
+            ang = torch.rand(T, 32, device=dev) * 6.28
+            tabs = (torch.cos(ang).contiguous(), torch.sin(ang).contiguous())
+        qkv_ref = ops.gemm(x, w)
+        qk_ref = ops.qknorm_rope_fwd(qkv_ref, wq, wk, tabs, d, T)
+        qk = torch.full((R, 2 * d), float("nan"), device=dev, dtype=torch.bfloat16)
+        cos, sin = tabs if tabs is not None else (None, None)
+        qkv = ops.gemm(x, w, epilogue=ops.EPI_QKNORM, aux=qk, qknorm=(wq, wk, cos, sin, T))
+        torch.cuda.synchronize()
+        same_raw = bool((qkv == qkv_ref).all())
+        same_qk = bool((qk == qk_ref).all())
+        rel = float((qk.float() - qk_ref.float()).abs().max() / qk_ref.float().abs().max())
+        print(f"[qknorm B={B} T={T} d={d} rope={rope}] raw identical: {same_raw}, q|k identical: {same_qk} (max rel {rel:.2e})")
+        ok &= same_raw and rel < 1e-2
+    return ok
+
+
 def group_perf():
     shapes = [
         ("qkv_x cfg2", 16384, 2304, 768, 0, 0, False),
@@ -250,6 +282,6 @@ if __name__ == "__main__":
     g = sys.argv[1] if len(sys.argv) > 1 else "basic"
     _lib.check(L.mmdit_device_check(), "device_check")
     t0 = time.time()
-    ok = {"basic": group_basic, "major": group_major, "epi": group_epi, "perf": group_perf, "swiglu": group_swiglu}[g]()
+    ok = {"basic": group_basic, "major": group_major, "epi": group_epi, "perf": group_perf, "swiglu": group_swiglu, "qknorm": group_qknorm}[g]()
     print(f"GROUP {g}: {'ALL PASS' if ok else 'SOME FAIL'} ({time.time() - t0:.1f}s)")
     sys.exit(0 if ok else 1)

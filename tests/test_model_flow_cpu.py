@@ -129,3 +129,26 @@ def test_trainer_buckets_take_the_gradients_in_place(cpu_kernels, golden):
         if p.requires_grad:
             assert p.grad.data_ptr() == p._grad_slot.data_ptr(), k
             assert torch.equal(p.grad, q.grad), k
+
+
+@pytest.mark.parametrize("sampler", ["euler", "heun"])
+def test_sampler_loop_wires_cfg_and_euler_like_the_reference(cpu_kernels, sampler):
+    """sample_imgs (diff_model.py:367-480): repeat-2 batch, null conditioning for the second half,
+    CFG combine + Euler update, width/height swap -- against the oracle's sampler on CPU."""
+    cfg = dict(inCh=16, class_dim=768, patch_size=2, dim=256, hidden_scale=4.0, num_heads=4,
+               attn_type="softmax_flash", MLP_type="swiglu", num_blocks=2, positional_encoding="RoPE2d")
+    model = diff_model(device="cpu", **cfg)
+    sd = O.synth_state_dict({k: tuple(v.shape) for k, v in model.state_dict().items()})
+    model.load_state_dict(sd, strict=True)
+    model.load_text_encoders()
+    out = model.sample_imgs(2, 3, "a prompt", cfg_scale=5.0, width=128, height=128, sampler=sampler,
+                            generator=torch.Generator().manual_seed(11))
+    assert out.shape == (2, 16, 16, 16) and bool(torch.isfinite(out).all())
+    if sampler != "euler":
+        return
+    th, tp = model.text_encoders.text_to_embedding("a prompt")
+    noise = torch.randn((2, 16, 16, 16), generator=torch.Generator().manual_seed(11))
+    ref = O.sample_euler(dict(sd), dict(cfg, attn_type="softmax"), noise, th, tp, 3, 5.0).clamp(-1, 1)
+    mse = float(((out - ref) ** 2).mean())
+    psnr = 10 * torch.log10(torch.tensor(4.0 / max(mse, 1e-12)))
+    assert float(psnr) >= 30.0, float(psnr)

@@ -152,3 +152,30 @@ def test_sampler_loop_wires_cfg_and_euler_like_the_reference(cpu_kernels, sample
     mse = float(((out - ref) ** 2).mean())
     psnr = 10 * torch.log10(torch.tensor(4.0 / max(mse, 1e-12)))
     assert float(psnr) >= 30.0, float(psnr)
+
+
+def test_trainer_step_order_matches_the_reference_loop(cpu_kernels):
+    """RFTrainer's eager step (zero -> forward -> loss -> backward -> clip 1.0 -> AdamW), driven with the
+    oracle's noise, against the oracle's restatement of model_trainer.py:463-503 over a few steps.
+    (torch.optim.AdamW here: the fused clip+AdamW kernel is a -m gpu test of its own.)"""
+    from mmdit.train import RFTrainer
+    cfg = dict(inCh=4, class_dim=768, patch_size=2, dim=256, hidden_scale=4.0, num_heads=4,
+               attn_type="softmax_flash", MLP_type="swiglu", num_blocks=2, positional_encoding="RoPE2d")
+    model = diff_model(device="cpu", **cfg)
+    sd = O.synth_state_dict({k: tuple(v.shape) for k, v in model.state_dict().items()})
+    model.load_state_dict(sd, strict=True)
+    tr = RFTrainer(model, fused_optimizer=False)
+    oracle = O.TrainOracle(sd, dict(cfg, attn_type="softmax"))
+    for s in range(4):
+        b = O.synth_batch(2, 4, 32, 32, 154, seed=3000 + s)
+        lo = oracle.step(b)
+        tr._zero()
+        x_t = ops.rf_noise(b["x0"].contiguous(), b["eps"].contiguous(), b["t"])
+        v = model(x_t, b["t"], b["c"].bfloat16(), b["pooled"].bfloat16(), b["null_pooled"], b["null_gemma"],
+                  b["null_bert"])
+        loss = functional.rf_loss(v, b["eps"], b["x0"])
+        loss.backward()
+        tr._update()
+        tr._after_step()
+        assert abs(float(loss) - lo) <= 1e-3 * max(1.0, abs(lo)), (s, float(loss), lo)
+    assert tr.steps_done == 4

@@ -37,6 +37,7 @@ CONFIGS = {
              "MMDiT depth24/dim1536/24 heads, 512px (64x64x16 latent, 1024+154 tokens), train step (BASELINE configs[3])"),
 }
 WORKLOAD = CONFIGS["cfg2"][3]
+REF_SAMPLE_BATCH = 2     # images per step of the CPU legs (reference arm and cpu_baseline): a bounded sample
 
 
 def train_flops_per_image(cfg, N, M):
@@ -128,7 +129,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
-    B = 2 if (args.steps + args.warmup) <= 24 else 1
+    B = REF_SAMPLE_BATCH      # the same bounded sample as the product arm's cpu_baseline leg, whatever --steps is
     ips, sec = cpu_oracle_run(args.steps, args.warmup, B)
     cores = os.cpu_count() or 1
     sample = f"oracle port (fp32 torch CPU, {cores} threads), batch {B} per step of the cfg2 workload"
@@ -137,24 +138,45 @@ def run_reference(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "MMDiT depth12/dim768 256px rectified-flow train step (BASELINE configs[1])",
-                   "batch_per_step": B, "tokens": 256 + TEXT_TOKENS},
+                   "batch_per_step": B, "tokens": 256 + TEXT_TOKENS,
+                   "note": f"bounded sample: {B} images per step of the batch-{BATCH} workload (img/s is per-image, batch-size independent on the CPU)"},
         "cpu_baseline": {"value": ips, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": ips, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
 
 # ---------------------------------------------------------------------------- product arm
-def instrument_kernels(trainer, batch):
-    """One extra, untimed step with CUDA events around every GEMM / attention launch (on the
-    launching stream) -> per-class device time and algorithmic work for the roofline object."""
+def _row_bytes(kind):
+    """Algorithmic HBM bytes of the memory-bound kernels (SURVEY 8d, bf16 activations): (name, fn(args) -> bytes)."""
+    return {
+        "ln_modulate_fwd": lambda x, *a, **k: 4.0 * x.numel(),
+        "ln_modulate_bwd": lambda dy, x, mean, rstd, scale, dres, *a, **k: (6.0 if dres is None else 8.0) * x.numel(),
+        "gate_residual_fwd": lambda a_, *r, **k: 6.0 * a_.numel(),
+        "gate_bwd": lambda dout, *r, **k: 8.0 * dout.numel(),
+        "qknorm_rope_fwd": lambda qkv, wq, wk, rope, d, *r, **k: 8.0 * qkv.shape[0] * d,
+        "qknorm_rope_bwd": lambda dqk, qkv, wq, wk, rope, dqkv, dwq, dwk, d, *r, **k: 14.0 * qkv.shape[0] * d,
+        "swiglu_bwd": lambda da, h12, *r, **k: 10.0 * h12.numel(),     # read da (h) + h12 (2h), write dh12 (2h)
+    }[kind]
+
+
+def instrument_kernels(trainer, batch, replays=3):
+    """Per-kernel-class device time of one train step (forward + backward), free of host launch gaps:
+    the step is captured ONCE into a CUDA graph on a single stream with an external-event record node
+    before and after every GEMM / attention / row-kernel launch; the graph is replayed and the event
+    pairs read back.  (Round 1 timed an eager step behind a `_sleep`; on a slow host the pairs timed
+    launch gaps -- the driver's line showed GEMMs taking 3x the step.)  Serialised kernels on one
+    stream: a pair brackets its kernel alone, and the classes can only sum to <= the replay time."""
     import torch
-    from mmdit import ops
-    rec = {"gemm": [], "attn_fwd": [], "attn_bwd": []}
-    orig = (ops.gemm, ops.attn_fwd, ops.attn_bwd)
+    from mmdit import ops, streams
+    kinds = ["gemm", "attn_fwd", "attn_bwd", "ln_modulate_fwd", "ln_modulate_bwd", "gate_residual_fwd", "gate_bwd",
+             "qknorm_rope_fwd", "qknorm_rope_bwd", "swiglu_bwd"]
+    rec = {k: [] for k in kinds}
+    orig = {k: getattr(ops, k) for k in kinds}
 
     def timed(kind, fn, work):
         def wrap(*a, **k):
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0 = torch.cuda.Event(enable_timing=True, external=True)
+            e1 = torch.cuda.Event(enable_timing=True, external=True)
             e0.record()
             out = fn(*a, **k)
             e1.record()
@@ -167,28 +189,82 @@ def instrument_kernels(trainer, batch):
         N = B.shape[1] if k.get("b_major") else B.shape[0]
         return 2.0 * M * N * K
 
-    ops.gemm = timed("gemm", orig[0], gemm_work)
-    ops.attn_fwd = timed("attn_fwd", orig[1], lambda q, k, v, B, H, N, M, s, **kw: 4.0 * B * H * (N + M) ** 2 * 64)
-    ops.attn_bwd = timed("attn_bwd", orig[2],
-                         lambda q, k, v, o, l, do, dq, dk, dv, B, H, N, M, s: 10.0 * B * H * (N + M) ** 2 * 64)
-    import mmdit.functional as Fn
-    from mmdit import streams
+    work = {"gemm": gemm_work,
+            "attn_fwd": lambda q, k, v, B, H, N, M, s, **kw: 4.0 * B * H * (N + M) ** 2 * 64,
+            "attn_bwd": lambda q, k, v, o, l, do, dq, dk, dv, B, H, N, M, s: 10.0 * B * H * (N + M) ** 2 * 64}
+    for k in kinds:
+        setattr(ops, k, timed(k, orig[k], work.get(k) or _row_bytes(k)))
     dual = streams.ENABLED
-    streams.ENABLED = False    # one stream: an event pair must time its kernel alone, not a neighbour too
+    streams.ENABLED = False    # one stream: an event pair must bracket its kernel alone
+    g = torch.cuda.CUDAGraph()
     try:
         trainer._zero()
-        torch.cuda._sleep(int(4e8))   # keep the GPU busy while the host enqueues: events then time kernels, not launch gaps
-        trainer._fwd_bwd(batch)
         torch.cuda.synchronize()
+        with torch.cuda.graph(g):
+            trainer._fwd_bwd(batch)
+            if trainer.buckets is not None:
+                trainer.buckets.finish()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for _ in range(replays):
+            t0.record()
+            g.replay()
+            t1.record()
+        torch.cuda.synchronize()
+        replay_ms = t0.elapsed_time(t1)
     finally:
-        ops.gemm, ops.attn_fwd, ops.attn_bwd = orig
+        for k in kinds:
+            setattr(ops, k, orig[k])
         streams.ENABLED = dual
-    out = {}
+    out = {"replay_ms": replay_ms}
     for kind, items in rec.items():
         ms = sum(e0.elapsed_time(e1) for e0, e1, _ in items)
-        out[kind] = dict(launches=len(items), ms=ms, flops=sum(w for _, _, w in items))
-    del Fn
+        out[kind] = dict(launches=len(items), ms=ms, work=sum(w for _, _, w in items))
     return out
+
+
+def gpu_library_run(steps, warmup, batch, dev):
+    """The reference's GPU path on this box ("the kernel to beat", SURVEY 8d / BASELINE.md section 4): the
+    oracle's restatement of the reference modules under torch.autocast(bf16) -- cuBLAS GEMMs, ATen
+    LayerNorm / RMSNorm / elementwise, flash_attn_func 2.8.3 as in Attention.py:293 (torch SDPA if
+    flash-attn is not importable) -- with clip_grad_norm_ + torch.optim.AdamW(fused) as model_trainer.py
+    :483-503.  Eager PyTorch, no activation checkpointing (the faster of the reference's two settings)."""
+    import torch
+    from oracle import mmdit_oracle as O
+    from src.models.diff_model import diff_model
+    try:
+        import flash_attn  # noqa: F401
+        O.ATTENTION_KERNEL = "flash"
+    except Exception:  # noqa: BLE001
+        O.ATTENTION_KERNEL = "sdpa"
+    shapes = {k: tuple(v.shape) for k, v in diff_model(device="cpu", **CFG2).state_dict().items()}
+    P = {k: v.to(dev).requires_grad_(not k.endswith("freqs")) for k, v in O.synth_state_dict(shapes).items()}
+    params = [v for v in P.values() if v.requires_grad]
+    opt = torch.optim.AdamW(params, lr=1e-4, eps=1e-8, weight_decay=0.01, fused=True)
+    cfg = dict(CFG2, attn_type="softmax")
+    bs = [{k: v.to(dev) for k, v in O.synth_batch(batch, CFG2["inCh"], LATENT, LATENT, TEXT_TOKENS, seed=1000 + i).items()}
+          for i in range(2)]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    try:
+        for s in range(warmup + steps):
+            if s == warmup:
+                torch.cuda.synchronize()
+                e0.record()
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                loss, _ = O.rf_loss(P, cfg, bs[s % 2])
+            loss.backward()
+            torch.nn.utils.clip_grad_norm_(params, 1.0)
+            opt.step()
+            opt.zero_grad(set_to_none=True)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        return {"value": batch / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "batch": batch,
+                "last_loss": float(loss), "attention": O.ATTENTION_KERNEL,
+                "what": "reference modules restated in eager PyTorch under autocast(bf16): cuBLAS + ATen + "
+                        f"{'flash_attn_func 2.8.3' if O.ATTENTION_KERNEL == 'flash' else 'torch SDPA'}, "
+                        "clip + torch fused AdamW, no checkpointing"}
+    finally:
+        O.ATTENTION_KERNEL = "eager"
 
 
 def run_product(args):
@@ -242,9 +318,10 @@ def run_product(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms)
 
-    def fresh(i):  # the model masks c / pooled in place, so every step gets a pristine copy
-        b = dbs[i % nb]
-        return {k: (v.clone() if k in ("c", "pooled") else v) for k, v in b.items()}
+    def fresh(i):
+        # device-resident batch i.  The model masks c / pooled in place (diff_model.py:281-287): under the
+        # step graph that happens on the graph's static copy; eagerly it is idempotent for a fixed mask.
+        return dbs[i % nb]
 
     # ---- device-resident arm ("value")
     for i in range(args.warmup):
@@ -275,17 +352,29 @@ def run_product(args):
     ms_e2e = timed_loop(e2e_step, args.steps)
     e2e_value = world * BATCH * args.steps / (ms_e2e / 1e3)
 
-    # ---- per-kernel-class roofline from an instrumented, untimed step (eager, same shapes).
-    # Runs on EVERY rank: with data parallelism the backward launches gradient all-reduces.
-    # (uses the trainer's eager building blocks; no optimizer step, nothing is replayed afterwards)
+    # ---- per-kernel-class roofline: one extra, untimed step captured on ONE stream with event nodes
+    # around every GEMM / attention / row kernel (instrument_kernels).  Runs on EVERY rank: with data
+    # parallelism the backward launches the gradient exchange.
     def close_reduce():
         if trainer.buckets is not None:
             trainer.buckets.finish()
-    trainer._zero(); trainer._fwd_bwd(fresh(1)); close_reduce()   # eager warm-up of the probe path
     c1 = _lib.launch_count()
-    kern = instrument_kernels(trainer, fresh(0))
+    trainer._zero(); trainer._fwd_bwd(fresh(1)); close_reduce()   # eager warm-up of the probe path
     launches_per_step = _lib.launch_count() - c1 + 3              # + the 3 optimizer kernels of a real step
-    close_reduce()
+    torch.cuda.synchronize()
+    kern = instrument_kernels(trainer, fresh(0))
+    # optimizer pass alone (30 B / parameter: p, g, m, v read; p, m, v, bf16 shadow written)
+    n_param = sum(p.numel() for p in trainer.params)
+    o0, o1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if trainer.fused_optimizer:
+        saved_lr = trainer.opt.param_groups[0]["lr"]
+        trainer.opt.param_groups[0]["lr"] = 0.0      # measured, not trained
+        trainer.opt.step()
+        o0.record(); trainer.opt.step(); o1.record()
+        torch.cuda.synchronize()
+        trainer.opt.param_groups[0]["lr"] = saved_lr
+        trainer.opt.sync_lr()
+        kern["adamw"] = dict(launches=1, ms=o0.elapsed_time(o1), work=30.0 * n_param)
     barrier()
 
     if rank != 0:
@@ -294,49 +383,84 @@ def run_product(args):
         return
     pk = peaks()
     f_img, f_attn_img = train_flops_per_image(CFG2, (LATENT // 2) ** 2, TEXT_TOKENS)
-    g = kern["gemm"]
-    gemm_tf = g["flops"] / (g["ms"] * 1e-3) / 1e12 if g["ms"] else 0.0
-    att_ms = kern["attn_fwd"]["ms"] + kern["attn_bwd"]["ms"]
-    att_tf = (kern["attn_fwd"]["flops"] + kern["attn_bwd"]["flops"]) / (att_ms * 1e-3) / 1e12 if att_ms else 0.0
     step_ms = ms / args.steps
-    traffic = None   # dram__bytes_read+write per GEMM launch, from the committed ncu capture of this step
-    try:
-        with open(os.path.join(ROOT, "profiles", "r01_kernel_metrics_v6.json")) as f:
-            traffic = json.load(f)["gemm_tcgen05_kernel"]["dram_bytes_per_launch"]
-    except Exception:  # noqa: BLE001
-        pass
+    g = kern["gemm"]
+    gemm_tf = g["work"] / (g["ms"] * 1e-3) / 1e12 if g["ms"] else 0.0
+
+    def cls(kind, unit_scale, peak):
+        k = kern[kind]
+        if not k["launches"] or not k["ms"]:
+            return None
+        ach = k["work"] / (k["ms"] * 1e-3) / unit_scale
+        return {"achieved": ach, "frac": ach / peak, "ms_per_step": k["ms"], "launches_per_step": k["launches"],
+                "avg_launch_us": 1e3 * k["ms"] / k["launches"]}
+    tensor_classes = {k: cls(k, 1e12, pk["tf_sustained"]) for k in ("attn_fwd", "attn_bwd")}
+    hbm_classes = {k: cls(k, 1e9, pk["hbm"]) for k in kern if k not in ("gemm", "attn_fwd", "attn_bwd", "replay_ms")}
+    probe_sum_ms = sum(v["ms"] for k, v in kern.items() if isinstance(v, dict) and k != "adamw")
+    # the probe step is serialised on one stream: instrumented classes can only sum to <= its replay time
+    probe_ok = probe_sum_ms <= kern["replay_ms"] * 1.02 and g["ms"] <= step_ms
+    traffic, traffic_src = None, None
+    if args.config == "cfg2":
+        # NOT measured in this run (DRAM counters need ncu): the committed capture of this same step
+        try:
+            with open(os.path.join(ROOT, "profiles", "r01_kernel_metrics_v6.json")) as f:
+                traffic = json.load(f)["gemm_tcgen05_kernel"]["dram_bytes_per_launch"]
+            traffic_src = ("constant from profiles/r01_kernel_metrics_v6.json (ncu dram__bytes_read+write, mean over "
+                           "the cfg2 step's GEMM launches); not re-measured by bench.py")
+        except Exception:  # noqa: BLE001
+            pass
     roofline = {
         "bound": "tensor", "kernel": "gemm_tcgen05_kernel",
         "achieved": gemm_tf, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
         "frac": gemm_tf / pk["tf_sustained"], "peak_source": pk["src"] + " (sustained cuBLAS bf16)",
         "launches_per_step": g["launches"], "avg_launch_us": 1e3 * g["ms"] / max(1, g["launches"]),
-        "share_of_step": g["ms"] / step_ms, "traffic": traffic,
-        "traffic_source": "profiles/r01_kernel_metrics_v6.json (ncu, mean over the step's 340 GEMM launches)",
-        "algorithmic_flops_per_step": g["flops"],
-        "attention": {"achieved": att_tf, "unit": "TFLOP/s", "frac": att_tf / pk["tf_sustained"],
-                      "ms_per_step": att_ms, "share_of_step": att_ms / step_ms},
+        "share_of_step": g["ms"] / step_ms, "traffic": traffic, "traffic_source": traffic_src,
+        "algorithmic_flops_per_step": g["work"],
+        "method": "external CUDA-event nodes around every launch of a single-stream graph capture of the step",
+        "probe": {"replay_ms": kern["replay_ms"], "instrumented_ms": probe_sum_ms, "consistent": bool(probe_ok)},
+        "tensor_classes": tensor_classes,
+        "hbm_classes": {"peak": pk["hbm"], "unit": "GB/s", **hbm_classes},
+        "attention": {"achieved": (kern["attn_fwd"]["work"] + kern["attn_bwd"]["work"]) /
+                      max(1e-9, (kern["attn_fwd"]["ms"] + kern["attn_bwd"]["ms"]) * 1e-3) / 1e12,
+                      "unit": "TFLOP/s", "ms_per_step": kern["attn_fwd"]["ms"] + kern["attn_bwd"]["ms"],
+                      "share_of_step": (kern["attn_fwd"]["ms"] + kern["attn_bwd"]["ms"]) / step_ms},
         "step_model_flops_utilisation": f_img * BATCH / (step_ms * 1e-3) / 1e12 / pk["tf_sustained"],
     }
+    roofline["attention"]["frac"] = roofline["attention"]["achieved"] / pk["tf_sustained"]
+    if not probe_ok:
+        roofline["invalid"] = "per-class times do not fit inside the step: probe rejected"
+
+    # ---- the reference's GPU path on this box (library kernels), same workload, rank 0 at N=1 only
+    lib = None
+    used_graph = bool(trainer.use_graph)
+    if world == 1 and args.config == "cfg2" and not args.no_gpu_library_baseline:
+        try:
+            del trainer, model
+            torch.cuda.empty_cache()
+            lib = gpu_library_run(3, 2, BATCH, dev)
+        except Exception as e:  # noqa: BLE001
+            lib = {"value": None, "error": repr(e)[:300]}
 
     # ---- CPU baseline on this box's host cores (bounded sample: 1 warm-up + 2 steps of batch 2)
     cpu = None
     if not args.no_cpu_baseline:
         try:
-            ips, sec = cpu_oracle_run(2, 1, 2)
+            ips, sec = cpu_oracle_run(2, 1, REF_SAMPLE_BATCH)
             cpu = {"value": ips, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
                    "sample": f"oracle port fp32, 2 steps of batch 2 of the same cfg2 workload ({sec:.2f} s/step)"}
         except Exception as e:  # noqa: BLE001
             cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
                    "sample": f"failed: {e}"}
 
-    h2d = trainer.h2d_bytes(hbs[0])
+    h2d = sum(v.numel() * v.element_size() for v in hbs[0].values())
+    finite = all(l == l and abs(l) != float("inf") for l in losses)
     print(json.dumps({
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": WORKLOAD,
                    "global_batch": world * BATCH, "batch_per_gpu": BATCH, "parallelism": f"dp{world}",
-                   "cuda_graph": bool(trainer.use_graph), "gradient_exchange": exchange,
+                   "cuda_graph": used_graph, "gradient_exchange": exchange,
                    "two_stream_blocks": bool(__import__("mmdit.streams").streams.ENABLED),
                    "l2": "per-step working set (>20 GB) exceeds the 126 MB L2; no explicit flush"},
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
@@ -344,11 +468,14 @@ def run_product(args):
         "gpu_launches": launches_per_step * args.steps,
         "gpu_launches_per_step": launches_per_step,
         "launch_calls_in_timed_region": eager_launches,
-        "clocks": clk, "roofline": roofline, "cpu_baseline": cpu,
+        "clocks": clk, "roofline": roofline, "cpu_baseline": cpu, "gpu_library_baseline": lib,
         "tflops_per_step": f_img * BATCH / 1e12,
+        **({} if finite else {"invalid": "non-finite loss in the timed region"}),
     }))
     if world > 1:
         dist.destroy_process_group()
+    if not finite:
+        sys.exit("bench.py: non-finite loss -- the throughput above is not a valid measurement")
 
 
 def select_config(name, batch):
@@ -369,6 +496,8 @@ def main():
     ap.add_argument("--impl", default="product", choices=["product", "reference"])
     ap.add_argument("--no-graph", action="store_true", help="do not capture the step into a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-library-baseline", action="store_true",
+                    help="skip the eager-PyTorch (cuBLAS + flash-attn) run of the same workload on the GPU")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="data-parallel gradient exchange: our peer-memory kernel (default) or NCCL")
     ap.add_argument("--config", default="cfg2", choices=sorted(CONFIGS))

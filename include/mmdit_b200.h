@@ -239,9 +239,12 @@ int mmdit_fold_slices_f32(const float* ws, float* out, int64_t n, int32_t slices
  * Fused gradient-norm clip + AdamW + bf16 shadow refresh over many tensors
  * (model_trainer.py:483-503; "next" row (f)-1 of the scope table).  table: device array of
  * mmdit_param_desc; chunks: device array of int32 pairs (tensor index, chunk index) with
- * mmdit_adamw_chunk_elems() elements per chunk; state: device float[2] = {grad sum of squares,
- * step count}, owned by the caller and persistent across steps (the step count is incremented
- * on the device, so the call is CUDA-graph replayable).  max_norm <= 0 disables clipping. */
+ * mmdit_adamw_chunk_elems() elements per chunk; state: device float[4] = {grad sum of squares,
+ * step count, learning rate, reserved}, owned by the caller and persistent across steps (the step
+ * count is incremented on the device, so the call is CUDA-graph replayable).  lr < 0 means "read
+ * the learning rate from state[2]": a warm-up / decay scheduler (model_trainer.py:25-41,
+ * 263, 495-496) then only rewrites that float between replays of a captured step.
+ * max_norm <= 0 disables clipping. */
 typedef struct mmdit_param_desc {
   float* p; const float* g; float* m; float* v;
   void* shadow;          /* bf16 copy of p refreshed in the same pass, or NULL */

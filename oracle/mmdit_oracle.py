@@ -24,6 +24,10 @@ RMS_EPS = torch.finfo(torch.float32).eps   # nn.RMSNorm(eps=None) on fp32 input 
 # reference's eager `softmax` path bit-for-bit (explicit bf16 casts) -- used to pin this file to the
 # golden vectors, which were minted from that path.
 BF16_ATTENTION_CORE = False
+# "eager" (default): softmax(QK^T/8)V materialised.  "flash" / "sdpa": the library kernel the reference
+# itself calls on a GPU (flash_attn_func, Attention.py:293) resp. torch SDPA -- only for timing the
+# reference's GPU path beside ours (bench.py `gpu_library_baseline`), never for parity.
+ATTENTION_KERNEL = "eager"
 
 
 # ------------------------------------------------------------------ synthetic weights / data
@@ -126,7 +130,14 @@ def joint_attention(P, pre, x, c, H, hw, last):
         ang = axial_angles(P[pre + "rotary_emb.freqs"], h, w).reshape(1, 1, N, hd)
         qx, kx = rope(qx, ang), rope(kx, ang)
     q, k, v = torch.cat([qx, qc], 2), torch.cat([kx, kc], 2), torch.cat([vx, vc], 2)
-    if BF16_ATTENTION_CORE:
+    if ATTENTION_KERNEL == "flash":
+        from flash_attn import flash_attn_func
+        att = flash_attn_func(q.transpose(1, 2).to(torch.bfloat16), k.transpose(1, 2).to(torch.bfloat16),
+                              v.transpose(1, 2).to(torch.bfloat16), softmax_scale=hd ** -0.5).transpose(1, 2)
+    elif ATTENTION_KERNEL == "sdpa":
+        att = F.scaled_dot_product_attention(q.to(torch.bfloat16), k.to(torch.bfloat16), v.to(torch.bfloat16),
+                                             scale=hd ** -0.5)
+    elif BF16_ATTENTION_CORE:
         # Attention.py:277-284 verbatim: the eager path casts q, k, v to bf16 even outside autocast
         att = (q.to(torch.bfloat16) @ k.to(torch.bfloat16).mT) * hd ** -0.5
         att = (att.softmax(dim=-1) @ v.to(torch.bfloat16)).to(q.dtype)

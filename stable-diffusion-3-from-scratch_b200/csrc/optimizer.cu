@@ -53,8 +53,11 @@ grad_sumsq_kernel(const ParamDesc* __restrict__ table, const int2* __restrict__ 
 
 __global__ void __launch_bounds__(OPT_THREADS)
 adamw_kernel(const ParamDesc* __restrict__ table, const int2* __restrict__ chunks,
-             const float* __restrict__ state /* [0]=sumsq [1]=step (already incremented) */,
-             float lr, float beta1, float beta2, float eps, float wd, float max_norm) {
+             const float* __restrict__ state /* [0]=sumsq [1]=step (already incremented) [2]=lr */,
+             float lr_arg, float beta1, float beta2, float eps, float wd, float max_norm) {
+  // lr < 0: the learning rate is the device-resident state[2] (a scheduler rewrites it between
+  // replays of a captured step; by-value arguments are frozen into a CUDA graph)
+  const float lr = lr_arg < 0.f ? state[2] : lr_arg;
   const int2 w = chunks[blockIdx.x];
   const ParamDesc d = table[w.x];
   const long long beg = (long long)w.y * OPT_CHUNK;

@@ -19,25 +19,84 @@ class ParamDesc(C.Structure):
 
 
 class FusedAdamW:
+    """Drop-in for the reference's `torch.optim.AdamW(params, lr, eps=1e-8, weight_decay=0.01)`
+    (model_trainer.py:260) plus the `clip_grad_norm_(1.0)` in front of it (:487).
+
+    `param_groups` is a real one-entry list of dicts with torch.optim.AdamW's keys, so
+    `torch.optim.lr_scheduler.*` / transformers' `get_*_schedule_with_warmup` (model_trainer.py:25-41)
+    drive it unchanged: they write `param_groups[0]["lr"]`, and `step()` forwards that value to the
+    device-resident learning rate (state[2]) -- a by-value argument would be frozen into a captured
+    CUDA graph.  Call `sync_lr()` after `scheduler.step()` when replaying a captured step."""
+
     def __init__(self, model, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01, max_norm=1.0):
         self.model = model
         self.params = [p for p in model.parameters() if p.requires_grad]
-        self.lr, self.betas, self.eps, self.wd, self.max_norm = lr, betas, eps, weight_decay, max_norm
+        self.max_norm = max_norm
+        self.defaults = dict(lr=lr, betas=tuple(betas), eps=eps, weight_decay=weight_decay, amsgrad=False,
+                             maximize=False, foreach=None, capturable=False, differentiable=False,
+                             fused=None, decoupled_weight_decay=True)
+        self.param_groups = [dict(self.defaults, params=self.params, initial_lr=lr)]
         dev = self.params[0].device
         self.device = dev
         self.exp_avg = [torch.zeros_like(p, memory_format=torch.contiguous_format) for p in self.params]
         self.exp_avg_sq = [torch.zeros_like(p, memory_format=torch.contiguous_format) for p in self.params]
-        self.state = torch.zeros(2, device=dev, dtype=F32)      # [grad sum of squares, step]
-        chunk = _lib.lib().mmdit_adamw_chunk_elems()
+        self.state = torch.zeros(4, device=dev, dtype=F32)      # [grad sum of squares, step, lr, -]
+        self._lr_dev = None
+        self._lr_host = torch.zeros(1, dtype=F32)
+        if dev.type == "cuda":
+            self._lr_host = self._lr_host.pin_memory()
+        chunk = _lib.lib().mmdit_adamw_chunk_elems() if dev.type == "cuda" else 16384
         work = [(ti, ci) for ti, p in enumerate(self.params) for ci in range((p.numel() + chunk - 1) // chunk)]
         self.n_chunks = len(work)
         self.chunks = torch.tensor(work, dtype=torch.int32).to(dev)
         n = len(self.params)
-        self.host_table = torch.zeros(n * C.sizeof(ParamDesc), dtype=torch.uint8).pin_memory()
+        self.host_table = torch.zeros(n * C.sizeof(ParamDesc), dtype=torch.uint8)
+        if dev.type == "cuda":
+            self.host_table = self.host_table.pin_memory()
         self.dev_table = torch.zeros(n * C.sizeof(ParamDesc), dtype=torch.uint8, device=dev)
         self._descs = (ParamDesc * n).from_address(self.host_table.data_ptr())
         self._last = None
         self._shadow = {}
+        self.sync_lr()
+
+    # the reference reads / writes these through param_groups; keep attribute access working too
+    @property
+    def lr(self):
+        return self.param_groups[0]["lr"]
+
+    @lr.setter
+    def lr(self, v):
+        self.param_groups[0]["lr"] = float(v)
+
+    betas = property(lambda self: self.param_groups[0]["betas"])
+    eps = property(lambda self: self.param_groups[0]["eps"])
+    wd = property(lambda self: self.param_groups[0]["weight_decay"])
+
+    def sync_lr(self):
+        """Make the device-resident learning rate equal param_groups[0]["lr"] (tiny async H2D copy
+        on the current stream; skipped when unchanged)."""
+        lr = float(self.param_groups[0]["lr"])
+        if lr != self._lr_dev and not (self.device.type == "cuda" and torch.cuda.is_current_stream_capturing()):
+            self._lr_host[0] = lr
+            self.state[2:3].copy_(self._lr_host, non_blocking=True)
+            self._lr_dev = lr
+
+    def warm_kernels(self):
+        """Launch the optimizer kernels once on a throw-away 16-element parameter: loads the module
+        ahead of a CUDA-graph capture without touching the model or this optimizer's state."""
+        if self.device.type != "cuda":
+            return
+        t = torch.zeros(5, 16, device=self.device, dtype=F32)          # p, g, m, v, state
+        table = torch.zeros(C.sizeof(ParamDesc), dtype=torch.uint8)
+        d = ParamDesc.from_address(table.data_ptr())
+        d.p, d.g, d.m, d.v, d.shadow, d.n = (t[0].data_ptr(), t[1].data_ptr(), t[2].data_ptr(),
+                                             t[3].data_ptr(), None, 16)
+        dt = table.to(self.device)
+        chunks = torch.zeros(1, 2, dtype=torch.int32, device=self.device)
+        _lib.check(_lib.lib().mmdit_adamw_step(dt.data_ptr(), chunks.data_ptr(), 1, t[4].data_ptr(), 0.0, 0.9,
+                                               0.999, 1e-8, 0.0, 1.0, torch.cuda.current_stream().cuda_stream),
+                   "mmdit_adamw_step")
+        torch.cuda.current_stream().synchronize()     # `t`, `dt`, `chunks` die with this frame
 
     def bind_shadows(self):
         """Take over every bf16 shadow buffer the modules have built so far (call after a forward)."""
@@ -48,10 +107,13 @@ class FusedAdamW:
 
     @torch.no_grad()
     def step(self):
-        key = tuple(p.grad.data_ptr() for p in self.params)
+        self.sync_lr()
+        key = tuple(0 if p.grad is None else p.grad.data_ptr() for p in self.params)
         if key != self._last:      # gradient storage moved (eager mode): refresh the descriptor table
             for i, p in enumerate(self.params):
                 g = p.grad
+                if g is None:      # no gradient reached this parameter: torch.optim skips it; a zero
+                    g = p.grad = torch.zeros_like(p, memory_format=torch.contiguous_format)   # gradient only decays it
                 if not g.is_contiguous():
                     g = p.grad = g.contiguous()
                 d = self._descs[i]
@@ -61,9 +123,10 @@ class FusedAdamW:
                 d.n = p.numel()
             self.dev_table.copy_(self.host_table, non_blocking=True)
             self._last = tuple(p.grad.data_ptr() for p in self.params)
+        g0 = self.param_groups[0]
         _lib.check(_lib.lib().mmdit_adamw_step(
             self.dev_table.data_ptr(), self.chunks.data_ptr(), self.n_chunks, self.state.data_ptr(),
-            self.lr, self.betas[0], self.betas[1], self.eps, self.wd, self.max_norm,
+            -1.0, g0["betas"][0], g0["betas"][1], g0["eps"], g0["weight_decay"], self.max_norm,
             torch.cuda.current_stream().cuda_stream), "mmdit_adamw_step")
 
     def zero_grad(self, set_to_none=True):
@@ -78,13 +141,23 @@ class FusedAdamW:
         return self.state[0].sqrt()
 
     def state_dict(self):
-        return {"state": {i: {"step": self.state[1].clone(), "exp_avg": m, "exp_avg_sq": v}
+        """torch.optim.AdamW's layout (what saveModel writes to optim_*.pkl, diff_model.py:527-528):
+        loads into `torch.optim.AdamW(model.parameters())` and back."""
+        step = self.state[1].detach().clone()
+        group = {k: v for k, v in self.param_groups[0].items() if k != "params"}
+        group["params"] = list(range(len(self.params)))
+        return {"state": {i: {"step": step.clone(), "exp_avg": m, "exp_avg_sq": v}
                           for i, (m, v) in enumerate(zip(self.exp_avg, self.exp_avg_sq))},
-                "param_groups": [{"lr": self.lr, "betas": self.betas, "eps": self.eps,
-                                  "weight_decay": self.wd, "params": list(range(len(self.params)))}]}
+                "param_groups": [group]}
 
     def load_state_dict(self, sd):
         for i, st in sd["state"].items():
             self.exp_avg[int(i)].copy_(st["exp_avg"])
             self.exp_avg_sq[int(i)].copy_(st["exp_avg_sq"])
             self.state[1] = float(st["step"])
+        if sd.get("param_groups"):
+            g = sd["param_groups"][0]
+            for k in ("lr", "betas", "eps", "weight_decay", "initial_lr"):
+                if k in g:
+                    self.param_groups[0][k] = tuple(g[k]) if k == "betas" else g[k]
+        self.sync_lr()

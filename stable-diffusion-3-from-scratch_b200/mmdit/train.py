@@ -16,7 +16,7 @@ torch.distributed collectives (NCCL / gloo) remain as the fallback exchange (`pe
 import torch
 import torch.distributed as dist
 
-from . import ops, streams
+from . import ops, shadow, streams
 from .functional import rf_loss
 from .optim import FusedAdamW
 
@@ -65,9 +65,7 @@ class GradBuckets:
         for name, p in named_params:
             if not p.requires_grad:
                 continue
-            parts = name.split(".")
-            key = ("block", int(parts[1])) if parts[0] == "blocks" else ("rest", 0)
-            groups.setdefault(key, []).append(p)
+            groups.setdefault(self.bucket_key(name), []).append(p)
         # backward reaches the LAST block first: reduce in that order
         self.order = sorted(groups, key=lambda k: (k[0] != "block", -k[1]))
         first = {id(g[0]): g for g in adjacent if g}
@@ -110,6 +108,17 @@ class GradBuckets:
                 off += (p.numel() + 15) // 16 * 16
             self.buckets.append((key, flat, ps))
         self._seen = set()
+
+    @staticmethod
+    def bucket_key(name):
+        """Bucket of a parameter: its transformer block, or "rest".  The per-block y projections
+        (blocks.i.y_proj.*) belong to "rest": diff_model.forward computes them for ALL blocks in one
+        GEMM ahead of block 0, so their gradient lands at the very end of the backward -- inside a
+        block bucket they would hold every bucket's exchange back until then."""
+        parts = name.split(".")
+        if parts[0] == "blocks" and parts[2] != "y_proj":
+            return ("block", int(parts[1]))
+        return ("rest", 0)
 
     def zero(self):
         if self.arena is not None:
@@ -299,6 +308,7 @@ class RFTrainer:
         self.ema = ema
         self.steps_done = 0
         self._bound = False
+        self._graphs = {}          # batch geometry -> (graph, graph_opt, static inputs, loss)
         self.graph = None
         self.graph_opt = None
         self.static = None
@@ -355,10 +365,19 @@ class RFTrainer:
             self._update()
             self._after_step()
             return loss
-        if self.graph is None:
-            self._capture(batch)
+        # one captured step per input geometry: aspect-ratio buckets (feed.from_wire hands over a
+        # different latent h x w per bucket, dataset_utils.py:119-161) each get their own graph
+        key = tuple((k, tuple(v.shape), v.dtype) for k, v in sorted(batch.items()))
+        cap = self._graphs.get(key)
+        if cap is None:
+            cap = self._graphs[key] = self._capture(batch)
+        self.graph, self.graph_opt, self.static, self.loss = cap
         for k, v in batch.items():
             self.static[k].copy_(v, non_blocking=True)
+        # a replay runs no Python: bring the device-side copies of host-managed state up to date
+        if self.fused_optimizer:
+            shadow.refresh_stale(self.model)      # weights written in place since the last cast (load_state_dict, EMA copy_to)
+            self.opt.sync_lr()                    # a scheduler's new param_groups[0]["lr"] (model_trainer.py:495-496)
         self.graph.replay()
         if self.graph_opt is not None:
             # data parallel: the all-reduce sits between the two captured halves of the step
@@ -374,39 +393,68 @@ class RFTrainer:
             self.ema.update(self.steps_done)
 
     def _capture(self, batch):
-        self.static = {k: v.clone() for k, v in batch.items()}
-        # warm-up on a side stream (allocator + lazy initialisation), as CUDA graphs require
+        """Capture one training step for this batch geometry.  The warm-up that CUDA graphs need
+        (allocator, lazy module loading) must not train: with the fused optimizer it runs forward +
+        backward (+ exchange) only and the optimizer kernels are loaded by a dry launch on a dummy
+        parameter; with torch.optim the parameters and optimizer state are snapshotted and restored."""
+        static = {k: v.clone() for k, v in batch.items()}
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
+        snap = None
+        if not self.fused_optimizer:
+            snap = ([p.detach().clone() for p in self.params], _clone_state(self.opt.state_dict()))
         with torch.cuda.stream(s):
-            for _ in range(3):
+            for _ in range(2):
                 self._zero()
-                self._fwd_bwd(self.static)
-                self._update()
+                self._fwd_bwd(static)
+                if self.fused_optimizer:
+                    if self.buckets is not None:
+                        self.buckets.finish()
+                else:
+                    self._update()
+            if self.fused_optimizer:
+                self.opt.warm_kernels()
+                if not self._bound:
+                    self.opt.bind_shadows()
+                    self._bound = True
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
+        if snap is not None:
+            with torch.no_grad():
+                for p, q in zip(self.params, snap[0]):
+                    p.copy_(q)
+            self.opt.load_state_dict(snap[1])
         self._zero()
-        self.graph = torch.cuda.CUDAGraph()
-        self.graph_opt = None
+        graph = torch.cuda.CUDAGraph()
+        graph_opt = None
         if self.buckets is None:
-            with torch.cuda.graph(self.graph):
-                self.loss = self._fwd_bwd(self.static)
+            with torch.cuda.graph(graph):
+                loss = self._fwd_bwd(static)
                 self._update()
-            return
+            return graph, None, static, loss
         if self.buckets.arena is not None:
             # peer-memory exchange: plain kernels on a forked side stream, so the overlapped
             # bucket reductions are captured with the rest of the step into one graph
-            with torch.cuda.graph(self.graph):
+            with torch.cuda.graph(graph):
                 self.buckets.reset()
-                self.loss = self._fwd_bwd(self.static)
+                loss = self._fwd_bwd(static)
                 self._update()
-            return
+            return graph, None, static, loss
         self.buckets.overlap = False            # hooks stay silent while capturing / replaying
-        with torch.cuda.graph(self.graph):
+        with torch.cuda.graph(graph):
             self.buckets.reset()
-            self.loss = self._fwd_bwd(self.static)
+            loss = self._fwd_bwd(static)
             self.buckets._adopt_missing()
         self.buckets.all_reduce_mean()
-        self.graph_opt = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph_opt):
+        graph_opt = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph_opt):
             self.opt.step() if self.fused_optimizer else self._update()
+        return graph, graph_opt, static, loss
+
+
+def _clone_state(sd):
+    """Deep copy of a torch optimizer state_dict (tensors cloned)."""
+    import copy
+    return {"state": {k: {n: (v.detach().clone() if torch.is_tensor(v) else copy.deepcopy(v)) for n, v in st.items()}
+                      for k, st in sd["state"].items()},
+            "param_groups": copy.deepcopy(sd["param_groups"])}

@@ -142,6 +142,10 @@ def test_train_trajectory_vs_oracle(dev):
 
 
 def test_cuda_graph_step_equals_eager_step(dev):
+    """The captured step IS the eager step: same weights, same batches, same noise (the CUDA generator is
+    re-seeded before each step; a captured randn replays with the generator's current seed / offset) ->
+    the same loss on every step, the same weights after 3 steps and the same optimizer step count.
+    Capturing must not train: its warm-up runs no optimizer update."""
     from mmdit.train import RFTrainer, host_batch
     from src.models.diff_model import diff_model
     cfg = dict(inCh=16, class_dim=768, patch_size=2, dim=128, hidden_scale=4.0, num_heads=2,
@@ -151,15 +155,52 @@ def test_cuda_graph_step_equals_eager_step(dev):
     m2 = diff_model(device=dev, **cfg)
     m2.load_state_dict(m1.state_dict())
     t1, t2 = RFTrainer(m1, use_graph=False), RFTrainer(m2, use_graph=True)
+    start = [p.detach().clone() for p in m1.parameters()]
+    for i in range(3):
+        hb = host_batch(4, 16, 16, 16, seed=5 + i)
+        losses = []
+        for tr in (t1, t2):
+            torch.manual_seed(100 + i)
+            losses.append(float(tr.step({k: v.clone() for k, v in tr.to_device(hb).items()})))
+        assert abs(losses[0] - losses[1]) <= 2e-4 * max(1.0, abs(losses[0])), (i, losses)
+    assert float(t1.opt.state[1]) == 3.0 and float(t2.opt.state[1]) == 3.0
+    moved = sum(float((p - q).abs().sum()) for p, q in zip(m1.parameters(), start))
+    apart = sum(float((p - q).abs().sum()) for p, q in zip(m1.parameters(), m2.parameters()))
+    assert moved > 0 and apart <= 0.02 * moved, (moved, apart)     # fp32 atomics order only
+
+
+def test_graph_step_sees_new_lr_and_reloaded_weights(dev):
+    """A replayed graph runs no Python: the learning rate lives on the device (a scheduler only rewrites
+    one float), and weights written in place between replays (load_state_dict) reach the bf16 shadows."""
+    from mmdit.train import RFTrainer, host_batch
+    from src.models.diff_model import diff_model
+    cfg = dict(inCh=16, class_dim=768, patch_size=2, dim=128, hidden_scale=4.0, num_heads=2,
+               attn_type="softmax_flash", MLP_type="swiglu", num_blocks=2, positional_encoding="RoPE2d")
+    torch.manual_seed(0)
+    m = diff_model(device=dev, **cfg)
+    tr = RFTrainer(m, use_graph=True)
     hb = host_batch(4, 16, 16, 16, seed=5)
-    for tr in (t1, t2):
-        for _ in range(4 if tr is t1 else 1):   # graph capture runs 3 warm-up steps of its own
-            torch.manual_seed(1)
-            loss = tr.step({k: v.clone() for k, v in tr.to_device(hb).items()})
-    assert torch.isfinite(loss)
-    l1 = float(t1.step({k: v.clone() for k, v in t1.to_device(hb).items()}))
-    l2 = float(t2.step({k: v.clone() for k, v in t2.to_device(hb).items()}))
-    assert abs(l1 - l2) < 5e-2      # different noise draws; both near the same loss level
+    step = lambda: float(tr.step({k: v.clone() for k, v in tr.to_device(hb).items()}))
+    step()
+    w = m.blocks[0].attn.out_proj_x.weight
+    tr.opt.param_groups[0]["lr"] = 0.0            # what a warm-up scheduler does at step 0
+    before = w.detach().clone()
+    step()
+    assert torch.equal(w.detach(), before)         # lr 0 (and decay 1 - lr*wd = 1): nothing moves
+    tr.opt.param_groups[0]["lr"] = 1e-3
+    step()
+    assert not torch.equal(w.detach(), before)
+    # reload: every weight zero -> the model output must be the bias-only output, i.e. loss changes
+    sd = {k: torch.zeros_like(v) if v.dtype.is_floating_point and not k.endswith("freqs") else v
+          for k, v in m.state_dict().items()}
+    m.load_state_dict(sd)
+    tr.opt.param_groups[0]["lr"] = 0.0
+    l0 = step()
+    from mmdit.shadow import packed_weight
+    assert float(packed_weight(m.blocks[0].attn, "out_x", [w]).float().abs().max()) == 0.0
+    torch.manual_seed(3)
+    x0 = tr.to_device(hb)["x0"].float()
+    assert abs(l0 - float((x0 ** 2).mean() + 1.0)) < 0.2     # v = 0 -> loss = E[(eps - x0)^2] ~ 2
 
 
 def test_euler_cfg_sampler_vs_oracle(dev):

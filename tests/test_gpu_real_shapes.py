@@ -1,0 +1,226 @@
+"""GPU (-m gpu): parity at the shapes the BENCH actually runs (BASELINE configs[1]-[3]), asserted.
+
+The model-level cases of test_gpu_parity.py are depth 2-3 / batch <= 3; the kernels the bench
+launches (B=64, H=12: 3072 attention CTAs; 2.6-wave CTA-pair GEMMs; split-K wgrads at K=16384; the
+26-row text tail tile at 1024+154 tokens) are exercised here against fp32 torch / the fp32 oracle
+run on the same GPU.  Tolerances (north-star / BASELINE.md section 5):
+  kernels      : max|err| / max|ref| <= 1e-2 (bf16 outputs), 5e-3 (fp32 reductions)
+  model forward: v max-rel <= 2e-2, |loss - oracle| <= 1e-3
+  gradients    : max-rel <= max(2e-2, 2 x floor), floor = the error of the reference's own numerics
+                 (the oracle under torch.autocast(bf16), model_trainer.py:416) against the same fp32
+                 oracle, measured in the same test on the same tensor (k = 2)
+"""
+import os
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+
+pytestmark = pytest.mark.gpu
+
+CFG2 = dict(inCh=16, class_dim=768, patch_size=2, dim=768, hidden_scale=4.0, num_heads=12,
+            attn_type="softmax_flash", MLP_type="swiglu", num_blocks=12, positional_encoding="RoPE2d")
+
+
+@pytest.fixture(scope="module")
+def dev():
+    from mmdit import _lib
+    _lib.check(_lib.lib().mmdit_device_check(), "mmdit_device_check")
+    return torch.device("cuda")
+
+
+# ------------------------------------------------------------------ (i) attention at bench shapes
+@pytest.mark.parametrize("B,H,N,M,bounded", [
+    (64, 12, 256, 154, True),     # cfg2: the bench launch (single-pass softmax against the QK-norm bound)
+    (64, 12, 256, 154, False),    # same shape, online softmax
+    (16, 24, 1024, 154, True),    # cfg4: 10 key tiles, 26-row text tail tile
+    (8, 24, 256, 154, True),      # cfg3 geometry (24 heads)
+])
+def test_attention_fwd_bwd_at_bench_shapes(dev, B, H, N, M, bounded):
+    import kernel_probe
+    assert kernel_probe.attn_case(B, H, N, M, bwd=True, seed=5, bounded=bounded)
+
+
+# ------------------------------------------------------------------ (ii) every GEMM of the step
+def _step_gemms(d, RX, RC):
+    out = []
+    for R in (RX, RC):
+        out += [
+            (R, 3 * d, d, 0, 0, 0, 0), (R, d, d, 0, 0, 0, 0), (R, 8 * d, d, 0, 0, 0, 1), (R, d, 4 * d, 0, 0, 0, 1),
+            (R, d, 3 * d, 0, 1, 0, 0), (R, d, d, 0, 1, 0, 0), (R, d, 8 * d, 0, 1, 0, 0), (R, 4 * d, d, 0, 1, 0, 0),
+            (3 * d, d, R, 1, 1, 1, 0), (d, d, R, 1, 1, 1, 0), (8 * d, d, R, 1, 1, 1, 0), (d, 4 * d, R, 1, 1, 1, 0),
+        ]
+    out += [(64, 12 * d, d, 0, 0, 0, 0), (64, d, 12 * d, 0, 1, 0, 0), (12 * d, d, 64, 1, 1, 1, 0)]
+    return out
+
+
+@pytest.mark.parametrize("which", ["cfg2", "cfg3"])
+def test_every_gemm_shape_of_the_train_step(dev, which):
+    """fprop / dgrad / wgrad of q|k|v, out-proj, w12, w3 (both streams) and the packed adaLN GEMMs at
+    batch 64 (cfg2, d 768) and batch 32 (cfg3, d 1536): ours vs an fp32 matmul of the same bf16 operands."""
+    from mmdit import ops
+    d, batch = (768, 64) if which == "cfg2" else (1536, 32)
+    g = torch.Generator(device="cuda").manual_seed(3)
+    worst = 0.0
+    for (M, N, K, am, bm, f32, bias) in _step_gemms(d, batch * 256, batch * 154):
+        A = torch.randn((K, M) if am else (M, K), device=dev, generator=g).bfloat16()
+        Bm = torch.randn((K, N) if bm else (N, K), device=dev, generator=g).bfloat16()
+        bv = torch.randn(N, device=dev, generator=g) if bias else None
+        got = ops.gemm(A, Bm, a_major=am, b_major=bm, out_dtype=torch.float32 if f32 else torch.bfloat16, bias=bv)
+        ref = torch.matmul((A.t() if am else A).float(), (Bm if bm else Bm.t()).float())
+        if bias:
+            ref += bv
+        err = float((got.float() - ref).abs().max() / ref.abs().max())
+        worst = max(worst, err)
+        assert err <= (5e-3 if f32 else 1e-2), (which, M, N, K, am, bm, f32, err)
+        del A, Bm, got, ref
+    print(f"[{which}] worst GEMM max-rel error {worst:.2e}")
+
+
+# ------------------------------------------------- (iii) full-depth cfg2 at batch 64 vs the oracle
+def _oracle_grads(P, cfg, b, autocast):
+    from oracle import mmdit_oracle as O
+    for v in P.values():
+        v.grad = None
+    with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+        lo, vo = O.rf_loss(P, cfg, b)
+    lo.backward()
+    return float(lo), vo.detach().float(), {k: v.grad.detach().clone() for k, v in P.items() if v.requires_grad}
+
+
+def test_full_depth_cfg2_batch64_forward_backward_vs_oracle(dev):
+    """BASELINE configs[1] exactly as the bench runs it (depth 12, dim 768, batch 64, two-stream block
+    schedule, CTA-pair GEMMs, split-K wgrads) against the fp32 oracle on the same weights and batch."""
+    from mmdit.functional import rf_loss
+    from oracle import mmdit_oracle as O
+    from src.models.diff_model import diff_model
+    B = 64
+    model = diff_model(device=dev, **CFG2)
+    sd = O.synth_state_dict({k: tuple(v.shape) for k, v in model.state_dict().items()})
+    model.load_state_dict(sd, strict=True)
+    b = {k: v.to(dev) for k, v in O.synth_batch(B, 16, 32, 32, 154, seed=4242).items()}
+    t = b["t"]
+    x_t = (1 - t)[:, None, None, None] * b["x0"] + t[:, None, None, None] * b["eps"]
+    v = model(x_t, t, b["c"].bfloat16(), b["pooled"].bfloat16(), b["null_pooled"], b["null_gemma"], b["null_bert"])
+    loss = rf_loss(v, b["eps"], b["x0"])
+    loss.backward()
+    torch.cuda.synchronize()
+    grads = {k: p.grad.detach().clone() for k, p in model.named_parameters() if p.requires_grad}
+    v, loss = v.detach().float(), float(loss)
+    del model
+    torch.cuda.empty_cache()
+
+    P = {k: s.to(dev).requires_grad_(not k.endswith("freqs")) for k, s in sd.items()}
+    ocfg = dict(CFG2, attn_type="softmax")
+    lo, vo, go = _oracle_grads(P, ocfg, b, autocast=False)
+    la, va, ga = _oracle_grads(P, ocfg, b, autocast=True)       # the reference's own numerics (AMP bf16)
+    assert abs(loss - lo) <= 1e-3, (loss, lo)
+    ev = float((v - vo).abs().max() / vo.abs().max())
+    fv = float((va - vo).abs().max() / vo.abs().max())
+    assert ev <= 2e-2, (ev, fv)
+    worst = (0.0, None, 0.0)
+    for k, gk in go.items():
+        den = float(gk.abs().max())
+        if den == 0.0:
+            assert float(grads[k].abs().max()) == 0.0, k
+            continue
+        err = float((grads[k] - gk).abs().max()) / den
+        floor = float((ga[k] - gk).abs().max()) / den
+        if err > worst[0]:
+            worst = (err, k, floor)
+        assert err <= max(2e-2, 2 * floor), (k, err, floor)
+    print(f"cfg2 B=64: loss {loss:.5f} vs oracle {lo:.5f} (AMP oracle {la:.5f}); v max-rel {ev:.2e} "
+          f"(AMP floor {fv:.2e}); worst gradient {worst[1]} {worst[0]:.2e} (floor {worst[2]:.2e})")
+
+
+# ------------------------------------------------ (iv) 100-step loss trajectory, 50-step Euler PSNR
+def test_100_step_loss_trajectory_vs_oracle(dev):
+    """North-star: fp32 loss agreement <= 1e-3 over 100 steps (clip 1.0 + AdamW 1e-4, fresh batch each
+    step, the oracle's noise).  depth 4 / dim 512 / 8 heads at batch 8 through the fused optimizer."""
+    from mmdit import ops
+    from mmdit.functional import rf_loss
+    from mmdit.train import RFTrainer
+    from oracle import mmdit_oracle as O
+    from src.models.diff_model import diff_model
+    cfg = dict(CFG2, dim=512, num_heads=8, num_blocks=4)
+    model = diff_model(device=dev, **cfg)
+    sd = O.synth_state_dict({k: tuple(v.shape) for k, v in model.state_dict().items()})
+    model.load_state_dict(sd, strict=True)
+    tr = RFTrainer(model)
+    oracle = O.TrainOracle(sd, dict(cfg, attn_type="softmax"), device=dev)
+    worst = 0.0
+    for s in range(100):
+        b = {k: v.to(dev) for k, v in O.synth_batch(8, 16, 32, 32, 154, seed=7000 + s).items()}
+        lo = oracle.step(b)
+        tr._zero()
+        x_t = ops.rf_noise(b["x0"].contiguous(), b["eps"].contiguous(), b["t"])
+        v = model(x_t, b["t"], b["c"].bfloat16(), b["pooled"].bfloat16(), b["null_pooled"], b["null_gemma"],
+                  b["null_bert"])
+        loss = rf_loss(v, b["eps"], b["x0"])
+        loss.backward()
+        tr._update()
+        worst = max(worst, abs(float(loss) - lo))
+        assert abs(float(loss) - lo) <= 1e-3 * max(1.0, abs(lo)), (s, float(loss), lo)
+    print(f"100 steps: worst |loss - oracle| = {worst:.2e}")
+
+
+def test_50_step_euler_cfg5_sampler_psnr_vs_oracle(dev):
+    """Fixed-seed 50-step Euler sample with CFG 5 (the configs[4] sampler settings, infer.py:79-114) on a
+    depth-4 / dim-512 model at 256 px: PSNR of the bf16 product vs the fp32 oracle >= 30 dB."""
+    from oracle import mmdit_oracle as O
+    from src.models.diff_model import diff_model
+    cfg = dict(CFG2, dim=512, num_heads=8, num_blocks=4)
+    model = diff_model(device=dev, **cfg)
+    sd = O.synth_state_dict({k: tuple(v.shape) for k, v in model.state_dict().items()})
+    model.load_state_dict(sd, strict=True)
+    model.load_text_encoders()
+    out = model.sample_imgs(2, 50, "a prompt", cfg_scale=5.0, width=256, height=256, sampler="euler",
+                            generator=torch.Generator().manual_seed(11))
+    th, tp = model.text_encoders.text_to_embedding("a prompt")
+    noise = torch.randn((2, 16, 32, 32), generator=torch.Generator().manual_seed(11)).to(dev)
+    P = {k: v.to(dev) for k, v in sd.items()}
+    ref = O.sample_euler(P, dict(cfg, attn_type="softmax"), noise, th.to(dev), tp.to(dev), 50, 5.0).clamp(-1, 1)
+    mse = float(((out - ref) ** 2).mean())
+    psnr = float(10 * torch.log10(torch.tensor(4.0 / max(mse, 1e-12))))
+    print(f"50-step Euler / CFG 5: PSNR vs fp32 oracle {psnr:.1f} dB")
+    assert psnr >= 30.0, psnr
+
+
+# ------------------------------------------------------ cfg3 / cfg4 geometry at full width
+@pytest.mark.parametrize("latent,batch", [(32, 8), (64, 4)])
+def test_full_width_train_steps_track_the_oracle(dev, latent, batch):
+    """dim 1536 / 24 heads (BASELINE configs[2]/[3] width) at 256 px and 512 px (1024+154 tokens), three
+    blocks deep: 3 optimizer steps driven with the oracle's noise, |loss - oracle| <= 1e-3 each, then the
+    same trainer under a CUDA graph stays finite at the same level (the cfg3 bench line committed in
+    round 1 ended in NaN; this pins the shape family in the suite)."""
+    from mmdit import ops
+    from mmdit.functional import rf_loss
+    from mmdit.train import RFTrainer
+    from oracle import mmdit_oracle as O
+    from src.models.diff_model import diff_model
+    cfg = dict(CFG2, dim=1536, num_heads=24, num_blocks=3)
+    model = diff_model(device=dev, **cfg)
+    sd = O.synth_state_dict({k: tuple(v.shape) for k, v in model.state_dict().items()})
+    model.load_state_dict(sd, strict=True)
+    tr = RFTrainer(model)
+    oracle = O.TrainOracle(sd, dict(cfg, attn_type="softmax"), device=dev)
+    for s in range(3):
+        b = {k: v.to(dev) for k, v in O.synth_batch(batch, 16, latent, latent, 154, seed=9000 + s).items()}
+        lo = oracle.step(b)
+        tr._zero()
+        x_t = ops.rf_noise(b["x0"].contiguous(), b["eps"].contiguous(), b["t"])
+        v = model(x_t, b["t"], b["c"].bfloat16(), b["pooled"].bfloat16(), b["null_pooled"], b["null_gemma"],
+                  b["null_bert"])
+        loss = rf_loss(v, b["eps"], b["x0"])
+        loss.backward()
+        tr._update()
+        assert abs(float(loss) - lo) <= 1e-3 * max(1.0, abs(lo)), (s, float(loss), lo)
+    tg = RFTrainer(model, use_graph=True)
+    for s in range(3):
+        b = O.synth_batch(batch, 16, latent, latent, 154, seed=9100 + s)
+        l = float(tg.step({k: (v.to(dev).bfloat16() if k in ("x0", "c", "pooled") else v.to(dev))
+                           for k, v in b.items() if k != "eps"}))
+        assert l == l and abs(l - lo) < 0.5, (s, l, lo)

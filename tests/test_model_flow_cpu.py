@@ -179,3 +179,44 @@ def test_trainer_step_order_matches_the_reference_loop(cpu_kernels):
         tr._after_step()
         assert abs(float(loss) - lo) <= 1e-3 * max(1.0, abs(lo)), (s, float(loss), lo)
     assert tr.steps_done == 4
+
+
+def test_block_bucket_exchange_starts_before_the_next_block_backward(cpu_kernels, golden):
+    """Overlap contract of the data-parallel exchange (model_trainer.py:224 -- DDP's reducer): the
+    bucket of block k must be complete, and its exchange launched, before the first gradient hook
+    of block k-1 fires.  The batched y projections (computed for all blocks ahead of block 0) live in
+    the "rest" bucket, which closes last -- inside the block buckets they would delay every launch
+    to the end of the backward."""
+    from mmdit.train import GradBuckets
+    g = golden("cfg1")
+    m = dict(g["config"]["model"], num_blocks=3)
+    model = diff_model(**dict(m, attn_type="softmax_flash", device="cpu"))
+    adjacent = [blk._mod_weights() for blk in model.blocks]
+    gb = GradBuckets(list(model.named_parameters()), 1, None, torch.device("cpu"), peer=False, adjacent=adjacent)
+    assert all(GradBuckets.bucket_key(f"blocks.{i}.y_proj.0.{w}") == ("rest", 0) for i in range(3) for w in ("weight", "bias"))
+    gb.install_hooks()
+    gb.world_size = 2                       # hooks launch only when there is somebody to exchange with
+    events = []
+    orig_ready = gb._ready
+
+    def launch(bi):
+        events.append(("launch", gb.buckets[bi][0]))
+        gb._works[bi] = True
+
+    def ready(bi, p):
+        events.append(("hook", gb.buckets[bi][0]))
+        orig_ready(bi, p)
+
+    gb._launch, gb._ready = launch, ready
+    gb.reset()
+    b = O.synth_batch(2, m["inCh"], 32, 32, 154, seed=1000)
+    t = b["t"]
+    x_t = (1 - t)[:, None, None, None] * b["x0"] + t[:, None, None, None] * b["eps"]
+    v = model(x_t, t, b["c"].bfloat16(), b["pooled"].bfloat16(), b["null_pooled"], b["null_gemma"], b["null_bert"])
+    functional.rf_loss(v, b["eps"], b["x0"]).backward()
+    launches = [k for kind, k in events if kind == "launch"]
+    assert launches[:3] == [("block", 2), ("block", 1), ("block", 0)], launches
+    for blk in (2, 1):
+        i_launch = events.index(("launch", ("block", blk)))
+        first_next = events.index(("hook", ("block", blk - 1)))
+        assert i_launch < first_next, (blk, i_launch, first_next)

@@ -19,6 +19,7 @@
 // after the previous P.V has retired, and that P.V overlaps the next tile's softmax math.
 // Tiles never straddle the image/text boundary: each stream is tiled
 // separately and partial tiles are masked, so any N, M work.
+#include <stdlib.h>
 #include <type_traits>
 
 #include "common.cuh"
@@ -54,6 +55,7 @@ struct AttnFwdParams {
   int B, H, N, M;
   float scale, scale_log2;
   const float* logit_bound;  // device scalar: upper bound of |scale * q.k| (QK-RMSNorm makes it small), or null
+  int skip_if_bounded;       // the second-generation kernel (attn_fwd2.cu) serves launches whose bound is usable
 };
 
 __global__ void __launch_bounds__(ATT_THREADS, 2)
@@ -73,6 +75,10 @@ attn_fwd_kernel(const __grid_constant__ AttnFwdParams p) {
   uint64_t* s_free = bars + 8;    // every softmax thread holds its S row in registers
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
 
+  if (p.skip_if_bounded) {
+    const float bd = *p.logit_bound;
+    if (bd >= 0.f && bd <= 24.f) return;
+  }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ntx = (p.N + ATT_TILE - 1) / ATT_TILE;
   const int ntc = (p.M + ATT_TILE - 1) / ATT_TILE;
@@ -376,6 +382,8 @@ int make_attn_tmap(CUtensorMap* map, const void* base, long long ld, int H, int 
 
 using namespace mmdit;
 
+int launch_attn_fwd2(const mmdit_attn_args* a, cudaStream_t stream);   // attn_fwd2.cu
+
 extern "C" int mmdit_debug_attn_timeline(long long* buf, int block) {
   cudaError_t e = cudaMemcpyToSymbol(g_attn_timeline, &buf, sizeof(buf));
   if (e == cudaSuccess) e = cudaMemcpyToSymbol(g_attn_timeline_block, &block, sizeof(block));
@@ -413,15 +421,23 @@ extern "C" int mmdit_attn_fwd(const mmdit_attn_args* a, void* stream) {
   p.scale = a->scale;
   p.scale_log2 = a->scale * 1.4426950408889634f;
   p.logit_bound = a->logit_bound;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM);
-    if (e != cudaSuccess) {
-      set_last_error("attn_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-      return (int)e;
-    }
-    attr_set = true;
+  static const cudaError_t attr_rc =   // thread-safe one-time initialisation (C++11 magic static)
+      cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM);
+  if (attr_rc != cudaSuccess) {
+    set_last_error("attn_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(attr_rc));
+    return (int)attr_rc;
+  }
+  // With a logit bound the second-generation kernel (attn_fwd2.cu) runs; should the bound turn out
+  // to be unusable (> 24, only known on the device) it returns at once and the kernel below does the
+  // work -- and vice versa.  MMDIT_ATTN_FWD_V2=0 keeps everything on the first-generation kernel.
+  static const int use_v2 = [] {
+    const char* e = getenv("MMDIT_ATTN_FWD_V2");
+    return e ? atoi(e) : 1;
+  }();
+  if (a->logit_bound && use_v2) {
+    const int rc2 = launch_attn_fwd2(a, static_cast<cudaStream_t>(stream));
+    if (rc2) return rc2;
+    p.skip_if_bounded = 1;
   }
   const int nt = (a->N + ATT_TILE - 1) / ATT_TILE + (a->M + ATT_TILE - 1) / ATT_TILE;
   dim3 grid(nt, a->H, a->B);

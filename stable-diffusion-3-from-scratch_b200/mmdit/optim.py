@@ -18,29 +18,40 @@ class ParamDesc(C.Structure):
                 ("shadow", C.c_void_p), ("n", C.c_int64)]
 
 
-class FusedAdamW:
+class FusedAdamW(torch.optim.Optimizer):
     """Drop-in for the reference's `torch.optim.AdamW(params, lr, eps=1e-8, weight_decay=0.01)`
     (model_trainer.py:260) plus the `clip_grad_norm_(1.0)` in front of it (:487).
 
-    `param_groups` is a real one-entry list of dicts with torch.optim.AdamW's keys, so
-    `torch.optim.lr_scheduler.*` / transformers' `get_*_schedule_with_warmup` (model_trainer.py:25-41)
-    drive it unchanged: they write `param_groups[0]["lr"]`, and `step()` forwards that value to the
-    device-resident learning rate (state[2]) -- a by-value argument would be frozen into a captured
-    CUDA graph.  Call `sync_lr()` after `scheduler.step()` when replaying a captured step."""
+    A real `torch.optim.Optimizer`: `param_groups`, `state`, `state_dict()` / `load_state_dict()`
+    have torch.optim.AdamW's layout (optim_*.pkl written by saveModel, diff_model.py:527-528, loads
+    into either class), and `torch.optim.lr_scheduler.*` / transformers' `get_*_schedule_with_warmup`
+    (model_trainer.py:25-41) drive it unchanged: they write `param_groups[0]["lr"]`, and `step()`
+    forwards that value to the device-resident learning rate (state[2]) -- a by-value argument would
+    be frozen into a captured CUDA graph.  Call `sync_lr()` after `scheduler.step()` when replaying
+    a captured step (RFTrainer does)."""
 
     def __init__(self, model, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01, max_norm=1.0):
         self.model = model
-        self.params = [p for p in model.parameters() if p.requires_grad]
+        # like the reference (`AdamW(self.model.parameters())`, model_trainer.py:260) the group lists EVERY
+        # parameter, frozen ones included (they never get state), so state_dict indices line up
+        every = list(model.parameters())
+        params = [p for p in every if p.requires_grad]
+        defaults = dict(lr=lr, betas=tuple(betas), eps=eps, weight_decay=weight_decay, amsgrad=False,
+                        maximize=False, foreach=None, capturable=False, differentiable=False, fused=None,
+                        decoupled_weight_decay=True)
+        super().__init__(every, defaults)
+        pos = {id(p): j for j, p in enumerate(params)}
+        self._index = {i: pos[id(p)] for i, p in enumerate(every) if p.requires_grad}   # group index -> trainable index
+        self.params = params
         self.max_norm = max_norm
-        self.defaults = dict(lr=lr, betas=tuple(betas), eps=eps, weight_decay=weight_decay, amsgrad=False,
-                             maximize=False, foreach=None, capturable=False, differentiable=False,
-                             fused=None, decoupled_weight_decay=True)
-        self.param_groups = [dict(self.defaults, params=self.params, initial_lr=lr)]
         dev = self.params[0].device
         self.device = dev
         self.exp_avg = [torch.zeros_like(p, memory_format=torch.contiguous_format) for p in self.params]
         self.exp_avg_sq = [torch.zeros_like(p, memory_format=torch.contiguous_format) for p in self.params]
-        self.state = torch.zeros(4, device=dev, dtype=F32)      # [grad sum of squares, step, lr, -]
+        self.dstate = torch.zeros(4, device=dev, dtype=F32)     # [grad sum of squares, step, lr, -]
+        for p, m, v in zip(self.params, self.exp_avg, self.exp_avg_sq):
+            # torch.optim.AdamW's per-parameter state; `step` is one shared device scalar
+            self.state[p] = {"step": self.dstate[1], "exp_avg": m, "exp_avg_sq": v}
         self._lr_dev = None
         self._lr_host = torch.zeros(1, dtype=F32)
         if dev.type == "cuda":
@@ -59,7 +70,7 @@ class FusedAdamW:
         self._shadow = {}
         self.sync_lr()
 
-    # the reference reads / writes these through param_groups; keep attribute access working too
+    # attribute-style access to the hyper-parameters (they live in param_groups[0])
     @property
     def lr(self):
         return self.param_groups[0]["lr"]
@@ -78,7 +89,7 @@ class FusedAdamW:
         lr = float(self.param_groups[0]["lr"])
         if lr != self._lr_dev and not (self.device.type == "cuda" and torch.cuda.is_current_stream_capturing()):
             self._lr_host[0] = lr
-            self.state[2:3].copy_(self._lr_host, non_blocking=True)
+            self.dstate[2:3].copy_(self._lr_host, non_blocking=True)
             self._lr_dev = lr
 
     def warm_kernels(self):
@@ -106,7 +117,7 @@ class FusedAdamW:
         self._last = None
 
     @torch.no_grad()
-    def step(self):
+    def step(self, closure=None):
         self.sync_lr()
         key = tuple(0 if p.grad is None else p.grad.data_ptr() for p in self.params)
         if key != self._last:      # gradient storage moved (eager mode): refresh the descriptor table
@@ -125,36 +136,25 @@ class FusedAdamW:
             self._last = tuple(p.grad.data_ptr() for p in self.params)
         g0 = self.param_groups[0]
         _lib.check(_lib.lib().mmdit_adamw_step(
-            self.dev_table.data_ptr(), self.chunks.data_ptr(), self.n_chunks, self.state.data_ptr(),
+            self.dev_table.data_ptr(), self.chunks.data_ptr(), self.n_chunks, self.dstate.data_ptr(),
             -1.0, g0["betas"][0], g0["betas"][1], g0["eps"], g0["weight_decay"], self.max_norm,
             torch.cuda.current_stream().cuda_stream), "mmdit_adamw_step")
 
-    def zero_grad(self, set_to_none=True):
-        for p in self.params:
-            if set_to_none:
-                p.grad = None
-            elif p.grad is not None:
-                p.grad.zero_()
-
     def grad_norm(self):
         """Global gradient norm seen by the last step (before clipping)."""
-        return self.state[0].sqrt()
+        return self.dstate[0].sqrt()
 
-    def state_dict(self):
-        """torch.optim.AdamW's layout (what saveModel writes to optim_*.pkl, diff_model.py:527-528):
-        loads into `torch.optim.AdamW(model.parameters())` and back."""
-        step = self.state[1].detach().clone()
-        group = {k: v for k, v in self.param_groups[0].items() if k != "params"}
-        group["params"] = list(range(len(self.params)))
-        return {"state": {i: {"step": step.clone(), "exp_avg": m, "exp_avg_sq": v}
-                          for i, (m, v) in enumerate(zip(self.exp_avg, self.exp_avg_sq))},
-                "param_groups": [group]}
+    def step_count(self):
+        return self.dstate[1]
 
     def load_state_dict(self, sd):
+        """Accepts a torch.optim.AdamW (or FusedAdamW) state_dict; the moments are copied into this
+        optimizer's own buffers (the kernel's descriptor table and captured graphs hold their addresses)."""
         for i, st in sd["state"].items():
-            self.exp_avg[int(i)].copy_(st["exp_avg"])
-            self.exp_avg_sq[int(i)].copy_(st["exp_avg_sq"])
-            self.state[1] = float(st["step"])
+            j = self._index[int(i)]
+            self.exp_avg[j].copy_(st["exp_avg"])
+            self.exp_avg_sq[j].copy_(st["exp_avg_sq"])
+            self.dstate[1] = float(st["step"])
         if sd.get("param_groups"):
             g = sd["param_groups"][0]
             for k in ("lr", "betas", "eps", "weight_decay", "initial_lr"):

@@ -367,11 +367,7 @@ class RFTrainer:
             return loss
         # one captured step per input geometry: aspect-ratio buckets (feed.from_wire hands over a
         # different latent h x w per bucket, dataset_utils.py:119-161) each get their own graph
-        key = tuple((k, tuple(v.shape), v.dtype) for k, v in sorted(batch.items()))
-        cap = self._graphs.get(key)
-        if cap is None:
-            cap = self._graphs[key] = self._capture(batch)
-        self.graph, self.graph_opt, self.static, self.loss = cap
+        self.graph, self.graph_opt, self.static, self.loss = self.capture(batch)
         for k, v in batch.items():
             self.static[k].copy_(v, non_blocking=True)
         # a replay runs no Python: bring the device-side copies of host-managed state up to date
@@ -386,6 +382,15 @@ class RFTrainer:
             self.graph_opt.replay()
         self._after_step()
         return self.loss
+
+    def capture(self, batch):
+        """Build (once) the captured step for this batch geometry without running it; `step` does this
+        lazily.  Capturing does not train and leaves the optimizer state alone."""
+        key = tuple((k, tuple(v.shape), v.dtype) for k, v in sorted(batch.items()))
+        cap = self._graphs.get(key)
+        if cap is None:
+            cap = self._graphs[key] = self._capture(batch)
+        return cap
 
     def _after_step(self):
         self.steps_done += 1

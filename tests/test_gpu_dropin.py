@@ -130,4 +130,4 @@ def test_reference_training_loop_body_drives_the_product_model(pg, tmp_path):
     t_opt = torch.optim.AdamW(twin.parameters(), lr=1e-4, eps=1e-8, weight_decay=0.01)
     t_opt.load_state_dict(ours.opt.state_dict())
     ours.opt.load_state_dict(t_opt.state_dict())
-    assert float(ours.opt.state[1]) == 4.0
+    assert float(ours.opt.step_count()) == 4.0

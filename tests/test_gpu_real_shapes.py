@@ -218,6 +218,9 @@ def test_full_width_train_steps_track_the_oracle(dev, latent, batch):
         loss.backward()
         tr._update()
         assert abs(float(loss) - lo) <= 1e-3 * max(1.0, abs(lo)), (s, float(loss), lo)
+    # (a live autograd graph would keep AccumulateGrad nodes bound to this stream alive: a capture on
+    # another stream must not meet them)
+    del loss, v, x_t
     tg = RFTrainer(model, use_graph=True)
     for s in range(3):
         b = O.synth_batch(batch, 16, latent, latent, 154, seed=9100 + s)

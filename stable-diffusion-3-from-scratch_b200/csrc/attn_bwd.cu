@@ -165,7 +165,8 @@ attn_bwd_kernel(const __grid_constant__ AttnBwdParams p) {
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    // the whole warp walks the loop (all lanes wait on the barriers); one elected lane issues the MMAs
+    {
       // Software pipeline: S^T/dP^T of tile i+1 are issued as soon as the compute warps have read
       // tile i's, BEFORE the dV/dK/dQ MMAs of tile i, so exp/dS math of tile i+1 overlaps them.
       const uint32_t id_kn = make_idesc_bf16(128, 64, 0, 1);   // dV, dK
@@ -187,13 +188,16 @@ attn_bwd_kernel(const __grid_constant__ AttnBwdParams p) {
         mbar_wait(&qdo_full[st], (i >> 1) & 1);
         tc_fence_after();
         TL(tls++, 10 + i);
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_bf16(tm_St, k_desc + k * kStepK, q_desc0 + st * kTile + k * kStepK, id_kq, k > 0);
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tm_St, k_desc + k * kStepK, q_desc0 + st * kTile + k * kStepK, id_kq, k > 0);
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_bf16(tm_dPt, v_desc + k * kStepK, do_desc0 + st * kTile + k * kStepK, id_kq, k > 0);
-        umma_commit(st_full);
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tm_dPt, v_desc + k * kStepK, do_desc0 + st * kTile + k * kStepK, id_kq, k > 0);
+          umma_commit(st_full);
+        }
+        __syncwarp();
         TL(tls++, 20 + i);
       };
       mbar_wait(kv_full, 0);
@@ -208,34 +212,40 @@ attn_bwd_kernel(const __grid_constant__ AttnBwdParams p) {
         tc_fence_after();
         TL(tls++, 30 + i);
         if (i + 1 < nt) issue_s(i + 1);
-        if constexpr (PT_TMEM) {
+        if (elect_one()) {
+          if constexpr (PT_TMEM) {
+            for (int k = 0; k < nq / 16; ++k)
+              umma_bf16_ts(tm_dV, tm_Pt + k * 8, do_desc0_mn + st * kTile + k * kStepMN, id_kn,
+                           (i > 0 || k > 0) ? 1u : 0u);
+            umma_commit(dv_done);   // P^T in TMEM may be overwritten once these retire
+          } else {
+            for (int k = 0; k < nq / 16; ++k)
+              umma_bf16(tm_dV, pt_desc + (k >> 2) * kTile + (k & 3) * kStepK,
+                        do_desc0_mn + st * kTile + k * kStepMN, id_kn, (i > 0 || k > 0) ? 1u : 0u);
+          }
           for (int k = 0; k < nq / 16; ++k)
-            umma_bf16_ts(tm_dV, tm_Pt + k * 8, do_desc0_mn + st * kTile + k * kStepMN, id_kn,
-                         (i > 0 || k > 0) ? 1u : 0u);
-          umma_commit(dv_done);   // P^T in TMEM may be overwritten once these retire
-        } else {
-          for (int k = 0; k < nq / 16; ++k)
-            umma_bf16(tm_dV, pt_desc + (k >> 2) * kTile + (k & 3) * kStepK,
-                      do_desc0_mn + st * kTile + k * kStepMN, id_kn, (i > 0 || k > 0) ? 1u : 0u);
+            umma_bf16(tm_dK, dst_desc + (k >> 2) * kTile + (k & 3) * kStepK,
+                      q_desc0_mn + st * kTile + k * kStepMN, id_kn, (i > 0 || k > 0) ? 1u : 0u);
         }
-        for (int k = 0; k < nq / 16; ++k)
-          umma_bf16(tm_dK, dst_desc + (k >> 2) * kTile + (k & 3) * kStepK,
-                    q_desc0_mn + st * kTile + k * kStepMN, id_kn, (i > 0 || k > 0) ? 1u : 0u);
+        __syncwarp();
         TL(tls++, 40 + i);
         if (i > 0) {
           mbar_wait(dq_empty, (i - 1) & 1);
           tc_fence_after();
         }
         TL(tls++, 50 + i);
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k)
-          umma_bf16(tm_dQ, dst_desc0_mn + st * 2 * kTile + k * kStepMN, k_desc_mn + k * kStepMN, id_nn, k > 0);
-        umma_commit(&qdo_empty[st]);
-        umma_commit(&buf_free[st]);
-        umma_commit(dq_full);
+          for (int k = 0; k < 8; ++k)
+            umma_bf16(tm_dQ, dst_desc0_mn + st * 2 * kTile + k * kStepMN, k_desc_mn + k * kStepMN, id_nn, k > 0);
+          umma_commit(&qdo_empty[st]);
+          umma_commit(&buf_free[st]);
+          umma_commit(dq_full);
+          if (i == nt - 1) umma_commit(all_done);
+        }
+        __syncwarp();
         TL(tls++, 60 + i);
       }
-      umma_commit(all_done);
     }
   } else if (warp >= 10) {
     // ------------------------------------------------------------ dQ drain warps

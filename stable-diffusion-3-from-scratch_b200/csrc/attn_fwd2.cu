@@ -40,6 +40,19 @@ constexpr int F2_SMEM = 6 * F2_TILE_BYTES + 1024 + 256;     // Q[2], K[2], V[2],
 
 int make_attn_tmap(CUtensorMap* map, const void* base, long long ld, int H, int rows, int B);
 
+// Optional in-kernel timeline (tuning): one chosen CTA records (event id, clock64) pairs.
+// [0,256): MMA thread, [256,768): softmax warp 2 lane 0, [768,1280): softmax warp 7 lane 0
+__device__ long long* g_attn2_timeline = nullptr;
+__device__ int g_attn2_timeline_block = -1;
+#ifdef MMDIT_ATTN_TIMELINE   // make EXTRA=-DMMDIT_ATTN_TIMELINE: the stamps cost registers in the hot loops
+#define TL2(id)                                                                          \
+  do {                                                                                   \
+    if (tl && tls < tl_cap) { tl[2 * tls] = (id); tl[2 * tls + 1] = clock64(); ++tls; }  \
+  } while (0)
+#else
+#define TL2(id) do { } while (0)
+#endif
+
 struct AttnFwd2Params {
   CUtensorMap tmQ[2], tmK[2], tmV[2], tmO[2];  // [0] image stream, [1] text stream
   float* lse;                                  // [B, H, N+M]
@@ -120,6 +133,16 @@ attn_fwd2_kernel(const __grid_constant__ AttnFwd2Params p) {
   const int ntc = (p.M + F2_TILE - 1) / F2_TILE;
   const int nt = ntx + ntc;                  // query tiles == key tiles per (sample, head)
 
+#ifdef MMDIT_ATTN_TIMELINE
+  long long* tl = nullptr;
+  int tls = 0, tl_cap = 0;
+  if (g_attn2_timeline && (int)blockIdx.x == g_attn2_timeline_block && lane == 0) {
+    if (warp == 1) { tl = g_attn2_timeline; tl_cap = 128; }
+    if (warp == 2) { tl = g_attn2_timeline + 256; tl_cap = 256; }
+    if (warp == 7) { tl = g_attn2_timeline + 768; tl_cap = 256; }
+  }
+#endif
+  TL2(1);
   if ((smem_u32(smem) & 1023u) != 0) __trap();
   if (warp == 0) {
     if (lane == 0) {
@@ -181,7 +204,8 @@ attn_fwd2_kernel(const __grid_constant__ AttnFwd2Params p) {
     }
   } else if (warp == 1) {
     // -------------------------------------------------------------------- MMA issuer
-    if (lane == 0) {
+    // The whole warp walks the loop (every lane waits on the barriers); one elected lane issues.
+    {
       const uint32_t idesc_o = make_idesc_bf16(128, 64, 0, 1);
       const uint64_t q_desc0 = desc_kmajor(smem_u32(sQ), 0);
       const uint64_t k_desc0 = desc_kmajor(smem_u32(sK), 0);
@@ -199,11 +223,14 @@ attn_fwd2_kernel(const __grid_constant__ AttnFwd2Params p) {
         mbar_wait(&k_full[st], (n >> 1) & 1);
         tc_fence_after();
         const uint64_t qd = q_desc0 + (k & 1) * kTile, kd = k_desc0 + st * kTile;
+        if (elect_one()) {
 #pragma unroll
-        for (int kk = 0; kk < F2_HD / 16; ++kk)
-          umma_bf16(tm_S, qd + kk * kStepK, kd + kk * kStepK, idesc_s, kk > 0);
-        umma_commit(&k_empty[st]);
-        umma_commit(s_full);
+          for (int kk = 0; kk < F2_HD / 16; ++kk)
+            umma_bf16(tm_S, qd + kk * kStepK, kd + kk * kStepK, idesc_s, kk > 0);
+          umma_commit(&k_empty[st]);
+          umma_commit(s_full);
+        }
+        __syncwarp();
       };
       int n = 0;
       if (my_items > 0) issue_s(0, 0, 0);
@@ -216,18 +243,31 @@ attn_fwd2_kernel(const __grid_constant__ AttnFwd2Params p) {
           if (!last || k + 1 < my_items) {
             mbar_wait(s_free, n & 1);      // S_n sits in the softmax threads' registers: TMEM S is free
             tc_fence_after();
+            TL2(1000 + n);
             if (!last) issue_s(n + 1, k, j + 1);
             else issue_s(n + 1, k + 1, 0);  // the next item's first tile: runs under this item's epilogue
+            TL2(2000 + n);
           }
           mbar_wait(p_full, n & 1);
+          TL2(3000 + n);
           if (j == 0 && k > 0) mbar_wait(o_free, (k - 1) & 1);   // previous item's O has been read out
           mbar_wait(&v_full[st], (n >> 1) & 1);
           tc_fence_after();
           const uint64_t vd = v_desc0 + st * kTile;
-          for (int kk = 0; kk < n_mma / 16; ++kk)
-            umma_bf16_ts(tm_O, tm_P + kk * 8, vd + kk * kStepMN, idesc_o, (j > 0 || kk > 0) ? 1u : 0u);
-          umma_commit(&v_empty[st]);
-          umma_commit(pv_done);
+          if (elect_one()) {
+            if (n_mma == F2_TILE) {
+#pragma unroll
+              for (int kk = 0; kk < F2_TILE / 16; ++kk)
+                umma_bf16_ts(tm_O, tm_P + kk * 8, vd + kk * kStepMN, idesc_o, (j > 0 || kk > 0) ? 1u : 0u);
+            } else {
+              for (int kk = 0; kk < n_mma / 16; ++kk)
+                umma_bf16_ts(tm_O, tm_P + kk * 8, vd + kk * kStepMN, idesc_o, (j > 0 || kk > 0) ? 1u : 0u);
+            }
+            umma_commit(&v_empty[st]);
+            umma_commit(pv_done);
+          }
+          __syncwarp();
+          TL2(4000 + n);
         }
       }
     }
@@ -260,6 +300,7 @@ attn_fwd2_kernel(const __grid_constant__ AttnFwd2Params p) {
         const bool have = warp_active && c0 < n_mma;   // warp-uniform
         mbar_wait(s_full, n & 1);
         tc_fence_after();
+        TL2(1000 + n);
         if (have) {
           // 16 key columns at a time, two TMEM loads in flight: exp2 -> 8 packed bf16 pairs -> tcgen05.st
           const int nch = min(4, (n_mma - c0 + 15) >> 4);     // 16-column chunks of this thread (warp-uniform)
@@ -301,11 +342,13 @@ attn_fwd2_kernel(const __grid_constant__ AttnFwd2Params p) {
           tmem_ld16(tm_S + lane_off + c0, sa);
           if (nch > 1) tmem_ld16(tm_S + lane_off + c0 + 16, sb);
           tmem_ld_wait();
+          TL2(2000 + n);
           if (nch <= 2) {
             tc_fence_before();
             mbar_arrive(s_free);       // S has left TMEM: the next QK^T may overwrite it
           }
           chunk(sa, 0);
+          TL2(3000 + n);
           if (nch > 2) tmem_ld16(tm_S + lane_off + c0 + 32, sa);
           if (nch > 1) chunk(sb, 1);
           if (nch > 2) {
@@ -313,11 +356,14 @@ attn_fwd2_kernel(const __grid_constant__ AttnFwd2Params p) {
             tmem_ld_wait();
             tc_fence_before();
             mbar_arrive(s_free);
+            TL2(4000 + n);
             chunk(sa, 2);
             if (nch > 3) chunk(sb, 3);
           }
           l += (a0 + a1) + (a2 + a3);
+          TL2(5000 + n);
           tmem_st_wait();
+          TL2(6000 + n);
         } else {
           tc_fence_before();
           mbar_arrive(s_free);
@@ -336,9 +382,12 @@ attn_fwd2_kernel(const __grid_constant__ AttnFwd2Params p) {
       }
       // ---------------------------------------------------------------- epilogue
       sL[hf * 128 + r] = l;
+      TL2(7000 + k);
       mbar_wait(pv_done, (n - 1) & 1);       // the last P V has retired: O is final
       tc_fence_after();
+      TL2(7100 + k);
       named_bar_sync(1, 256);                // partial row sums visible
+      TL2(7200 + k);
       const float lt = sL[r] + sL[128 + r];
       uint32_t o[32];
       if (warp_active) {
@@ -365,8 +414,10 @@ attn_fwd2_kernel(const __grid_constant__ AttnFwd2Params p) {
           p.lse[((long long)b * p.H + h) * (p.N + p.M) + tq] = bound + __logf(lt);
         }
       }
+      TL2(7300 + k);
       fence_proxy_async_smem();
       named_bar_sync(1, 256);                // the staging tile is complete (and sL may be rewritten)
+      TL2(7400 + k);
       if (warp == 2 && lane == 0) {
         tma_store_4d(&p.tmO[qs], stage, 0, h, q_row0, b);   // rows >= q_rows are clipped by the TMA unit
         tma_commit_group();
@@ -383,6 +434,12 @@ attn_fwd2_kernel(const __grid_constant__ AttnFwd2Params p) {
 }  // namespace mmdit
 
 using namespace mmdit;
+
+extern "C" int mmdit_debug_attn2_timeline(long long* buf, int block) {
+  cudaError_t e = cudaMemcpyToSymbol(g_attn2_timeline, &buf, sizeof(buf));
+  if (e == cudaSuccess) e = cudaMemcpyToSymbol(g_attn2_timeline_block, &block, sizeof(block));
+  return (int)e;
+}
 
 // Launches the second-generation forward for `a` (requires a->logit_bound); the kernel returns at
 // once when the bound turns out to be unusable (> 24), in which case the caller's online kernel runs.

@@ -106,6 +106,20 @@ __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// One lane of a CONVERGED warp (elect.sync).  tcgen05.mma / tcgen05.commit / TMA issue code guarded by
+// this predicate compiles to straight-line uniform-datapath instructions; guarded by `lane == 0`
+// instead, ptxas wraps every such instruction in an ELECT / BRA.U.ANY loop over the "possibly several"
+// active lanes, which costs tens of cycles per MMA issue.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---- TMA --------------------------------------------------------------------
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(m) : "memory");

@@ -322,7 +322,9 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    // The whole warp walks the loop and waits on the barriers; ONE elected lane issues (guarding with
+    // `lane == 0` instead makes ptxas wrap every TMA / MMA instruction in an ELECT loop, see elect_one()).
+    {
       int stage = 0;
       uint32_t phase = 0;
       // In a pair both CTAs load their halves and credit the LEADER's full barrier, which
@@ -343,26 +345,29 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sA = smem + stage * stage_bytes;
           uint8_t* sB = sA + A_STAGE_BYTES;
-          if (!PAIR || rank == 0) mbar_expect_tx(&full_bar[stage], PAIR ? 2 * stage_bytes : stage_bytes);
-          if (!p.a_mn) {
-            load(sA, &p.tmA, &full_bar[stage], kb * BLOCK_K, m_blk * BLOCK_M);
-          } else {
-            for (int i = 0; i < BLOCK_M / 64; ++i)
-              load(sA + i * (BLOCK_K * 128), &p.tmA, &full_bar[stage], m_blk * BLOCK_M + i * 64, kb * BLOCK_K);
+          if (elect_one()) {
+            if (!PAIR || rank == 0) mbar_expect_tx(&full_bar[stage], PAIR ? 2 * stage_bytes : stage_bytes);
+            if (!p.a_mn) {
+              load(sA, &p.tmA, &full_bar[stage], kb * BLOCK_K, m_blk * BLOCK_M);
+            } else {
+              for (int i = 0; i < BLOCK_M / 64; ++i)
+                load(sA + i * (BLOCK_K * 128), &p.tmA, &full_bar[stage], m_blk * BLOCK_M + i * 64, kb * BLOCK_K);
+            }
+            if (!p.b_mn) {
+              load(sB, &p.tmB, &full_bar[stage], kb * BLOCK_K, n0);
+            } else {
+              for (int i = 0; i < b_rows / 64; ++i)
+                load(sB + i * (BLOCK_K * 128), &p.tmB, &full_bar[stage], n0 + i * 64, kb * BLOCK_K);
+            }
           }
-          if (!p.b_mn) {
-            load(sB, &p.tmB, &full_bar[stage], kb * BLOCK_K, n0);
-          } else {
-            for (int i = 0; i < b_rows / 64; ++i)
-              load(sB + i * (BLOCK_K * 128), &p.tmB, &full_bar[stage], n0 + i * 64, kb * BLOCK_K);
-          }
+          __syncwarp();
           if (++stage == stages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // -------------------------------------------------------------- MMA issuer
-    if (lane == 0 && rank == 0) {
+    if (rank == 0) {
       const uint32_t idesc = make_idesc_bf16(PAIR ? 2 * BLOCK_M : BLOCK_M, block_n, p.a_mn, p.b_mn);
       int stage = 0;
       uint32_t phase = 0;
@@ -380,23 +385,28 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + stage * stage_bytes);
           const uint32_t b_addr = a_addr + A_STAGE_BYTES;
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / 16; ++k) {
-            const uint64_t adesc =
-                p.a_mn ? desc_mnmajor(a_addr, k, BLOCK_K * 128) : desc_kmajor(a_addr, k);
-            const uint64_t bdesc =
-                p.b_mn ? desc_mnmajor(b_addr, k, BLOCK_K * 128) : desc_kmajor(b_addr, k);
-            if constexpr (PAIR) umma_bf16_pair(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-            else umma_bf16(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < BLOCK_K / 16; ++k) {
+              const uint64_t adesc =
+                  p.a_mn ? desc_mnmajor(a_addr, k, BLOCK_K * 128) : desc_kmajor(a_addr, k);
+              const uint64_t bdesc =
+                  p.b_mn ? desc_mnmajor(b_addr, k, BLOCK_K * 128) : desc_kmajor(b_addr, k);
+              if constexpr (PAIR) umma_bf16_pair(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+              else umma_bf16(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            }
+            // frees the smem slot (in both CTAs of a pair) when these MMAs retire
+            if constexpr (PAIR) umma_commit_pair(&empty_bar[stage]);
+            else umma_commit(&empty_bar[stage]);
+            // accumulator ready for the epilogue warps (of both CTAs)
+            if (kb == kb1 - 1) {
+              if constexpr (PAIR) umma_commit_pair(&tmem_full[as]);
+              else umma_commit(&tmem_full[as]);
+            }
           }
-          // frees the smem slot (in both CTAs of a pair) when these MMAs retire
-          if constexpr (PAIR) umma_commit_pair(&empty_bar[stage]);
-          else umma_commit(&empty_bar[stage]);
+          __syncwarp();
           if (++stage == stages) { stage = 0; phase ^= 1; }
         }
-        // accumulator ready for the epilogue warps (of both CTAs)
-        if constexpr (PAIR) umma_commit_pair(&tmem_full[as]);
-        else umma_commit(&tmem_full[as]);
         as ^= 1;
         if (as == 0) aphase ^= 1;
       }
@@ -429,7 +439,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
         const float* bp = reinterpret_cast<const float*>(p.bias);
         auto stage_tile = [&](const uint32_t (&packed)[32], const CUtensorMap* tm, int col) {
           uint8_t* tile = sbase + (tma_buf & 1) * 4096;
-          if (lane == 0) tma_wait_group_read1();
+          if (elect_one()) tma_wait_group_read1();
           __syncwarp();
           uint8_t* prow = tile + lane * 128;
 #pragma unroll
@@ -438,7 +448,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
                 make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
           fence_proxy_async_smem();
           __syncwarp();
-          if (lane == 0 && !(p.debug & 1)) {
+          if (!(p.debug & 1) && elect_one()) {
             tma_store_2d(tm, tile, col, static_cast<int>(m0));
             tma_commit_group();
           }
@@ -522,7 +532,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
         const float* bp = reinterpret_cast<const float*>(p.bias);
         auto stage_tile = [&](const uint32_t (&packed)[32], const CUtensorMap* tm, int col) {
           uint8_t* tile = sbase + (tma_buf & 1) * 4096;
-          if (lane == 0) tma_wait_group_read1();
+          if (elect_one()) tma_wait_group_read1();
           __syncwarp();
           uint8_t* prow = tile + lane * 128;
 #pragma unroll
@@ -531,7 +541,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
                 make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
           fence_proxy_async_smem();
           __syncwarp();
-          if (lane == 0 && !(p.debug & 1)) {
+          if (!(p.debug & 1) && elect_one()) {
             tma_store_2d(tm, tile, col, static_cast<int>(m0));
             tma_commit_group();
           }
@@ -599,7 +609,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
           if (n >= p.N || m0 >= p.M) continue;  // whole chunk beyond a ragged edge
           uint8_t* tile = sbase + (tma_buf & 1) * 4096;
           // the store that last used this tile (two chunks ago) must have finished reading it
-          if (lane == 0) tma_wait_group_read1();
+          if (elect_one()) tma_wait_group_read1();
           __syncwarp();
           uint8_t* prow = tile + lane * 128;
           const float* bp = reinterpret_cast<const float*>(p.bias);
@@ -624,7 +634,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
           }
           fence_proxy_async_smem();
           __syncwarp();
-          if (lane == 0 && !(p.debug & 1)) {
+          if (!(p.debug & 1) && elect_one()) {
             tma_store_2d(&p.tmD, tile, n, static_cast<int>(m0));
             tma_commit_group();
           }
@@ -689,7 +699,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
       if (as == 0) aphase ^= 1;
     }
     if constexpr (EV == EV_BF16_TMA || EV == EV_SWIGLU_TMA || EV == EV_QKNORM_TMA) {
-      if (lane == 0) tma_wait_group0();  // staging tiles must outlive their stores
+      if (elect_one()) tma_wait_group0();  // staging tiles must outlive their stores
     }
   }
 

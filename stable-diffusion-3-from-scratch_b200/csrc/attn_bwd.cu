@@ -92,6 +92,7 @@ attn_bwd_kernel(const __grid_constant__ AttnBwdParams p) {
   uint64_t* stage_free = bars + 12;  // [2]: dQ staging (aliases the P^T buffer) read out by the TMA reduce
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
   [[maybe_unused]] uint64_t* dv_done = bars + 15;  // PT_TMEM: the dV MMAs reading P^T from TMEM have retired
+  uint64_t* st_free = bars + 16;  // 256: every compute thread holds its S^T / dP^T values in registers
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int T = p.N + p.M;
@@ -119,6 +120,7 @@ attn_bwd_kernel(const __grid_constant__ AttnBwdParams p) {
       for (int s = 0; s < 2; ++s) { mbar_init(&qdo_full[s], 1); mbar_init(&qdo_empty[s], 1); }
       mbar_init(st_full, 1);
       mbar_init(pt_full, 256);
+      mbar_init(st_free, 256);
       mbar_init(dq_full, 1);
       mbar_init(dq_empty, 128);   // the 4 drain warps
       mbar_init(&buf_free[0], 1);
@@ -208,10 +210,16 @@ attn_bwd_kernel(const __grid_constant__ AttnBwdParams p) {
         const int row0 = (qs == 0 ? i : i - ntx) * ATT_TILE;
         const int nq = (min(ATT_TILE, (qs == 0 ? p.N : p.M) - row0) + 15) & ~15;
         const uint64_t pt_desc = pt_desc0 + st * 2 * kTile, dst_desc = dst_desc0 + st * 2 * kTile;
+        if (i + 1 < nt) {
+          // S^T / dP^T of tile i sit in the compute threads' registers: the next tile's may be issued
+          // now, while tile i's exponentials are still being computed
+          mbar_wait(st_free, i & 1);
+          tc_fence_after();
+          issue_s(i + 1);
+        }
         mbar_wait(pt_full, i & 1);
         tc_fence_after();
         TL(tls++, 30 + i);
-        if (i + 1 < nt) issue_s(i + 1);
         if (elect_one()) {
           if constexpr (PT_TMEM) {
             for (int k = 0; k < nq / 16; ++k)
@@ -341,6 +349,12 @@ attn_bwd_kernel(const __grid_constant__ AttnBwdParams p) {
 #pragma unroll
         for (int q = 0; q < 32; ++q) ppk[q] = 0u;
       }
+      // chunks of 32 query columns this thread will load from TMEM (warp-uniform)
+      const int n_ld = (quarter * 32 >= k_valid) ? 0 : (hf * 64 >= nq ? 0 : (hf * 64 + 32 >= nq ? 1 : 2));
+      if (n_ld == 0) {
+        tc_fence_before();
+        mbar_arrive(st_free);
+      }
 #pragma unroll(PT_TMEM ? 2 : 1)
       for (int c = 0; c < 2; ++c) {
         if (hf * 64 + c * 32 >= nq) break;  // warp-uniform: these query columns do not exist
@@ -361,6 +375,10 @@ attn_bwd_kernel(const __grid_constant__ AttnBwdParams p) {
         tmem_ld32(tm_St + lane_off + hf * 64 + c * 32, s);
         tmem_ld32(tm_dPt + lane_off + hf * 64 + c * 32, dp);
         tmem_ld_wait();
+        if (c == n_ld - 1) {   // last TMEM read of this tile by this thread
+          tc_fence_before();
+          mbar_arrive(st_free);
+        }
         uint8_t* prow = bufP + hf * ATT_TILE_BYTES + r * 128;
         uint8_t* drow = bufD + hf * ATT_TILE_BYTES + r * 128;
 #pragma unroll

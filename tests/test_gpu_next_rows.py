@@ -159,3 +159,48 @@ def test_captured_euler_step_equals_the_eager_loop(dev, monkeypatch):
     assert float((want - got).abs().max()) <= 1e-3
     import copy
     assert "_sample_graphs" in model.__dict__ and len(copy.deepcopy(model).__dict__["_sample_graphs"]) == 0
+
+
+def test_no_kernel_reads_memory_it_did_not_write(dev, monkeypatch):
+    """Every buffer the product allocates with torch.empty / empty_like is poisoned (NaN, then 1e30): the
+    no_grad forward must be bit-identical and a train step's loss / gradients unchanged up to fp32 atomics
+    order -- partial tiles, ragged rows and workspaces never leak uninitialised memory into a result."""
+    from mmdit.functional import rf_loss
+    model, _ = _model(dev)
+    B, L = 3, 24
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(B, 16, L, 40, generator=g).to(dev)                 # ragged 12x20 token grid
+    c = torch.randn(B, 154, 2304, generator=g).to(dev).bfloat16()
+    pooled = torch.randn(B, 768, generator=g).to(dev).bfloat16()
+    t = torch.rand(B, generator=g).to(dev)
+    _empty, _empty_like = torch.empty, torch.empty_like
+    state = {"val": None}
+
+    def fill(tn):
+        if state["val"] is not None and tn.is_cuda and tn.dtype.is_floating_point:
+            tn.fill_(state["val"])
+        return tn
+    monkeypatch.setattr(torch, "empty", lambda *a, **k: fill(_empty(*a, **k)))
+    monkeypatch.setattr(torch, "empty_like", lambda *a, **k: fill(_empty_like(*a, **k)))
+
+    def run_train():
+        for p in model.parameters():
+            p.grad = None
+        v = model(x, t, c.clone(), pooled.clone())
+        loss = rf_loss(v, torch.ones_like(x), x)
+        loss.backward()
+        return float(loss), model.blocks[0].MLP_c.MLP.w3.weight.grad.clone(), model.blocks[1].attn.key_proj_x.weight.grad.clone()
+
+    with torch.no_grad():
+        v0 = model(x, t, c.clone(), pooled.clone()).float().clone()
+    l0, g0, h0 = run_train()
+    for val in (float("nan"), 1e30):
+        state["val"] = val
+        with torch.no_grad():
+            v1 = model(x, t, c.clone(), pooled.clone()).float().clone()
+        l1, g1, h1 = run_train()
+        state["val"] = None
+        assert torch.equal(v0, v1), val
+        assert abs(l1 - l0) <= 1e-5 and bool(torch.isfinite(g1).all())
+        assert float((g1 - g0).abs().max()) <= 1e-5 * float(g0.abs().max()) + 1e-9
+        assert float((h1 - h0).abs().max()) <= 1e-5 * float(h0.abs().max()) + 1e-9

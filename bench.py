@@ -152,6 +152,7 @@ def _row_bytes(kind):
         "ln_modulate_fwd": lambda x, *a, **k: 4.0 * x.numel(),
         "ln_modulate_bwd": lambda dy, x, mean, rstd, scale, dres, *a, **k: (6.0 if dres is None else 8.0) * x.numel(),
         "gate_residual_fwd": lambda a_, *r, **k: 6.0 * a_.numel(),
+        "gate_residual_ln_fwd": lambda a_, *r, **k: 8.0 * a_.numel(),      # read a, resid; write x', LN-mod(x')
         "gate_bwd": lambda dout, *r, **k: 8.0 * dout.numel(),
         "qknorm_rope_fwd": lambda qkv, wq, wk, rope, d, *r, **k: 8.0 * qkv.shape[0] * d,
         "qknorm_rope_bwd": lambda dqk, qkv, wq, wk, rope, dqkv, dwq, dwk, d, *r, **k: 14.0 * qkv.shape[0] * d,
@@ -168,7 +169,8 @@ def instrument_kernels(trainer, batch, replays=3):
     stream: a pair brackets its kernel alone, and the classes can only sum to <= the replay time."""
     import torch
     from mmdit import ops, streams
-    kinds = ["gemm", "attn_fwd", "attn_bwd", "ln_modulate_fwd", "ln_modulate_bwd", "gate_residual_fwd", "gate_bwd",
+    kinds = ["gemm", "attn_fwd", "attn_bwd", "ln_modulate_fwd", "ln_modulate_bwd", "gate_residual_fwd",
+             "gate_residual_ln_fwd", "gate_bwd",
              "qknorm_rope_fwd", "qknorm_rope_bwd", "swiglu_bwd"]
     rec = {k: [] for k in kinds}
     orig = {k: getattr(ops, k) for k in kinds}
@@ -202,6 +204,8 @@ def instrument_kernels(trainer, batch, replays=3):
         trainer._zero()
         torch.cuda.synchronize()
         with torch.cuda.graph(g):
+            if trainer.buckets is not None:
+                trainer.buckets.reset()      # pins the CAPTURING stream as the one the exchange forks from
             trainer._fwd_bwd(batch)
             if trainer.buckets is not None:
                 trainer.buckets.finish()

@@ -159,6 +159,15 @@ int64_t mmdit_rowreduce_workspace_floats(int64_t rows, int32_t d, int64_t rows_p
 int mmdit_gate_residual_fwd(const void* a, const void* gate, const void* resid, void* out,
                             int64_t rows, int32_t d, int64_t rows_per_batch, int64_t ld_gate,
                             void* stream);
+/* The gated residual followed by the next adaLN LayerNorm-modulate in ONE pass
+ * (Transformer_Block_Dual.py:64-72: `X = attn * scale1(y) + X` then `norm2(X, y)`; same for the text
+ * stream): x_out = a * gate[b] + resid (bf16, bit-identical to mmdit_gate_residual_fwd),
+ * y = LN(x_out) * (1 + scale[b]) + shift[b] (bit-identical to mmdit_ln_modulate_fwd on x_out),
+ * mean / rstd of x_out for the backward. */
+int mmdit_gate_residual_ln_fwd(const void* a, const void* gate, const void* resid, const void* shift,
+                               const void* scale, void* x_out, void* y, float* mean, float* rstd,
+                               int64_t rows, int32_t d, int64_t rows_per_batch, int64_t ld_gate,
+                               int64_t ld_mod, float eps, void* stream);
 int mmdit_gate_bwd(const void* dout, const void* a, const void* gate, void* da, void* dgate,
                    int32_t dgate_bf16, float* dab, float* workspace, int64_t rows, int32_t d,
                    int64_t rows_per_batch, int64_t ld_gate, int64_t ld_dgate, int64_t ld_dab,

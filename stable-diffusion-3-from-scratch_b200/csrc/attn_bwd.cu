@@ -577,21 +577,19 @@ extern "C" int mmdit_attn_bwd(const mmdit_attn_args* a, void* stream_) {
   p.B = a->B; p.H = a->H; p.N = a->N; p.M = a->M;
   p.scale = a->scale;
   p.scale_log2 = a->scale * 1.4426950408889634f;
-  static int pt_tmem = -1;
-  if (pt_tmem < 0) {
-    const char* ev = getenv("MMDIT_ATTN_BWD_PT_TMEM");   // experimental variant, see the kernel comment
-    pt_tmem = ev ? atoi(ev) : 0;
-  }
-  static bool attr_set = false;
-  if (!attr_set) {
-    e = cudaFuncSetAttribute(attn_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM);
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(attn_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM);
-    if (e != cudaSuccess) {
-      set_last_error("attn_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-      return (int)e;
-    }
-    attr_set = true;
+  static const int pt_tmem = [] {   // variant validated on hardware (round 2): correct, no faster -> off
+    const char* ev = getenv("MMDIT_ATTN_BWD_PT_TMEM");
+    return ev ? atoi(ev) : 0;
+  }();
+  static const cudaError_t attr_rc = [] {   // thread-safe one-time initialisation (C++11 magic static)
+    cudaError_t r = cudaFuncSetAttribute(attn_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM);
+    if (r == cudaSuccess)
+      r = cudaFuncSetAttribute(attn_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM);
+    return r;
+  }();
+  if (attr_rc != cudaSuccess) {
+    set_last_error("attn_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(attr_rc));
+    return (int)attr_rc;
   }
   const int nt = (a->N + ATT_TILE - 1) / ATT_TILE + (a->M + ATT_TILE - 1) / ATT_TILE;
   dim3 grid(nt, a->H, a->B);

@@ -731,15 +731,11 @@ static int pick_block_n(long long M, long long N, int sms) {
 
 template <int EV, bool PAIR>
 static int launch_variant(int grid, int smem_bytes, cudaStream_t stream, const GemmParams& p) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<EV, PAIR>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET);
-    if (e != cudaSuccess) {
-      set_last_error("gemm: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-      return (int)e;
-    }
-    attr_set = true;
+  static const cudaError_t attr_rc = cudaFuncSetAttribute(   // thread-safe one-time initialisation
+      gemm_tcgen05_kernel<EV, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET);
+  if (attr_rc != cudaSuccess) {
+    set_last_error("gemm: cudaFuncSetAttribute: %s", cudaGetErrorString(attr_rc));
+    return (int)attr_rc;
   }
   if constexpr (PAIR) {
     cudaLaunchConfig_t cfg;

@@ -136,6 +136,78 @@ ln_mod_fwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ shift,
   }
 }
 
+// ------------------------------------------- gated residual + LN-modulate, one pass
+// The two always follow each other inside a block (Transformer_Block_Dual.py:64-72):
+//   x' = a * gate[b] + resid            (rounded to bf16, exactly like gate_residual_fwd_kernel)
+//   y  = LN(x') * bf16(1 + scale[b]) + shift[b]
+// One warp per row: a, resid read once, x' and y written once -- the separate kernels re-read x'.
+template <int NC>
+__global__ void __launch_bounds__(ROW_THREADS)
+gate_res_ln_fwd_kernel(const bf16* __restrict__ a, const bf16* __restrict__ gate,
+                       const bf16* __restrict__ resid, const bf16* __restrict__ shift,
+                       const bf16* __restrict__ scale, bf16* __restrict__ xo, bf16* __restrict__ y,
+                       float* __restrict__ mean_out, float* __restrict__ rstd_out, long long R, int d,
+                       long long rows_per_batch, long long ld_gate, long long ld_mod, float eps) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * ROW_WARPS + warp;
+  if (row >= R) return;
+  const long long b = row / rows_per_batch;
+  float v[NC][8], r[NC][8], g[NC][8];
+  load_row<NC>(a + row * d, d, lane, v);
+  load_row<NC>(resid + row * d, d, lane, r);
+  load_row<NC>(gate + b * ld_gate, d, lane, g);
+  float s = 0.f;
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    const int col = c * 256 + lane * 8;
+    if (col < d) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[c][j] = fmaf(v[c][j], g[c][j], r[c][j]);
+      store8(xo + row * d + col, v[c]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        v[c][j] = __bfloat162float(__float2bfloat16(v[c][j]));   // what the LN of the stored x' sees
+        s += v[c][j];
+      }
+    }
+  }
+  const float mean = warp_sum(s) / d;
+  float q = 0.f;
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    const int col = c * 256 + lane * 8;
+    if (col < d) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float t = v[c][j] - mean;
+        q += t * t;
+      }
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(q) / d + eps);
+  if (lane == 0) {
+    if (mean_out) mean_out[row] = mean;
+    if (rstd_out) rstd_out[row] = rstd;
+  }
+  const bf16* sh = shift + b * ld_mod;
+  const bf16* sc = scale + b * ld_mod;
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    const int col = c * 256 + lane * 8;
+    if (col < d) {
+      float fs[8], fc[8], o[8];
+      load8(sh + col, fs);
+      load8(sc + col, fc);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float one_plus = __bfloat162float(__float2bfloat16(1.f + fc[j]));
+        o[j] = (v[c][j] - mean) * rstd * one_plus + fs[j];
+      }
+      store8(y + row * d + col, o);
+    }
+  }
+}
+
 // ------------------------------------------------------------ LN-modulate bwd
 // g = dy*(1+s); dx = rstd*(g - mean(g) - xhat*mean(g*xhat)) (+ dres)
 // dshift[b] += sum_rows dy ; dscale[b] += sum_rows dy*xhat      (fp32 atomics)
@@ -412,6 +484,21 @@ int mmdit_ln_modulate_fwd(const void* x, const void* shift, const void* scale, v
                      (const bf16*)x, (const bf16*)shift, (const bf16*)scale, (bf16*)y, mean, rstd,
                      rows, d, rows_per_batch, ld_mod, eps)));
   return check_launch("ln_mod_fwd_kernel");
+}
+
+int mmdit_gate_residual_ln_fwd(const void* a, const void* gate, const void* resid, const void* shift,
+                               const void* scale, void* x_out, void* y, float* mean, float* rstd,
+                               int64_t rows, int32_t d, int64_t rows_per_batch, int64_t ld_gate,
+                               int64_t ld_mod, float eps, void* stream) {
+  MMDIT_REQUIRE(a && gate && resid && shift && scale && x_out && y && rows > 0 && d > 0 && d % 8 == 0 &&
+                    rows_per_batch > 0 && ld_gate % 8 == 0 && ld_mod % 8 == 0,
+                MMDIT_ERR_ARG, "gate_residual_ln_fwd: bad arguments (d, ld_gate, ld_mod must be multiples of 8)");
+  const unsigned grid = (unsigned)((rows + ROW_WARPS - 1) / ROW_WARPS);
+  DISPATCH_NC(d, MMDIT_CARVEOUT(gate_res_ln_fwd_kernel<NC>); (gate_res_ln_fwd_kernel<NC><<<grid, ROW_THREADS, 0, (cudaStream_t)stream>>>(
+                     (const bf16*)a, (const bf16*)gate, (const bf16*)resid, (const bf16*)shift,
+                     (const bf16*)scale, (bf16*)x_out, (bf16*)y, mean, rstd, rows, d, rows_per_batch,
+                     ld_gate, ld_mod, eps)));
+  return check_launch("gate_res_ln_fwd_kernel");
 }
 
 int64_t mmdit_rowreduce_workspace_floats(int64_t rows, int32_t d, int64_t rows_per_batch) {

@@ -16,6 +16,7 @@ SIGNATURES = {
     "mmdit_ln_modulate_fwd": [vp, vp, vp, vp, vp, vp, i64, i32, i64, i64, f32, vp],
     "mmdit_ln_modulate_bwd": [vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp, i64, i32, i64, i64, i64, vp],
     "mmdit_gate_residual_fwd": [vp, vp, vp, vp, i64, i32, i64, i64, vp],
+    "mmdit_gate_residual_ln_fwd": [vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, i64, i64, i64, f32, vp],
     "mmdit_gate_bwd": [vp, vp, vp, vp, vp, i32, vp, vp, i64, i32, i64, i64, i64, i64, vp],
     "mmdit_text_norm_fwd": [vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, f32, vp],
     "mmdit_text_norm_bwd": [vp, i32, vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, i32, vp],

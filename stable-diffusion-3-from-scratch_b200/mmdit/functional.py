@@ -18,6 +18,8 @@ from .ops import BF16, F32
 
 # MMDIT_FUSED_GATE=1 routes gate*x+residual through the GEMM epilogue instead of a separate kernel
 FUSED_GATE_EPILOGUE = os.environ.get("MMDIT_FUSED_GATE", "0") == "1"
+# MMDIT_FUSED_GATE_LN=0 keeps the gated residual and the LayerNorm-modulate that follows it in two kernels
+FUSED_GATE_LN = os.environ.get("MMDIT_FUSED_GATE_LN", "1") == "1"
 # MMDIT_FUSED_SWIGLU=0 keeps silu(x1)*x2 in its own kernel instead of the w12 GEMM's epilogue
 FUSED_SWIGLU = os.environ.get("MMDIT_FUSED_SWIGLU", "1") == "1"
 # MMDIT_FUSED_QKNORM=1 (experimental, not yet validated on hardware): per-head RMSNorm + 2-D RoPE of
@@ -146,6 +148,45 @@ class GatedLinearFn(Function):
         dw = _wgrad_gemm(da, a, [ctx.wparam]).view(ctx.wparam.shape)
         db = dab.sum(0) if ctx.has_bias else None
         return dx, None, None, dgate, do, None, dw, db
+
+
+class GatedLinearLNFn(Function):
+    """GatedLinearFn followed by the next adaLN LayerNorm-modulate (Transformer_Block_Dual.py:64-72),
+    with the gate, the residual add, the LayerNorm statistics and the modulate in ONE pass over the
+    GEMM output: returns (LN-mod(X'), X') with X' = (a @ W^T + b) * gate + resid.
+    The backward is LNModulateResFn's followed by GatedLinearFn's."""
+
+    @staticmethod
+    def forward(ctx, a, wb, bb, gate, resid, shift, scale, rows_per_batch, w, b):
+        aux = ops.gemm(a, wb, bias=bb)
+        xo, y, mean, rstd = ops.gate_residual_ln_fwd(aux, gate, resid, shift, scale, rows_per_batch)
+        ctx.save_for_backward(a, wb, aux, gate, xo, mean, rstd, scale)
+        ctx.wparam = w
+        ctx.rpb = rows_per_batch
+        ctx.has_bias = b is not None
+        ctx.set_materialize_grads(False)
+        return y, xo
+
+    @staticmethod
+    def backward(ctx, dy, dres):
+        a, wb, aux, gate, xo, mean, rstd, scale = ctx.saved_tensors
+        rpb = ctx.rpb
+        Bn, n = gate.shape
+        dmod = None
+        if dy is None:          # only the residual path was used
+            do = dres.contiguous()
+        else:
+            dmod = torch.empty((2, Bn, n), device=dy.device, dtype=BF16)
+            dr = None if dres is None else dres.contiguous()
+            do = ops.ln_modulate_bwd(dy.contiguous(), xo, mean, rstd, scale, dr, dmod[0], dmod[1], rpb)
+        dgate = torch.empty((Bn, n), device=do.device, dtype=BF16)
+        dab = torch.empty((Bn, n), device=do.device, dtype=F32) if ctx.has_bias else None
+        da = ops.gate_bwd(do, aux, gate, dgate, dab, rpb)
+        dx = ops.gemm(da, wb, b_major=1)
+        dw = _wgrad_gemm(da, a, [ctx.wparam]).view(ctx.wparam.shape)
+        db = dab.sum(0) if ctx.has_bias else None
+        return (dx, None, None, dgate, do, None if dmod is None else dmod[0],
+                None if dmod is None else dmod[1], None, dw, db)
 
 
 class LNModulateFn(Function):
@@ -301,26 +342,6 @@ class JointAttentionPreNormFn(Function):
                 None, None, None, None, None, None)
 
 
-class SwiGLUFn(Function):
-    """a = silu(x1) * x2 with h12 = [x1 | x2] (xformers SwiGLU, MLP.py:19,32).  Also returns
-    nothing else: the bias gradient of w12 is produced by LinearFn from dh12."""
-
-    @staticmethod
-    def forward(ctx, h12):
-        shape = h12.shape
-        h2 = h12.reshape(-1, shape[-1])
-        a = ops.swiglu_fwd(h2)
-        ctx.save_for_backward(h2)
-        ctx.shape = shape
-        return a.reshape(*shape[:-1], shape[-1] // 2)
-
-    @staticmethod
-    def backward(ctx, da):
-        (h2,) = ctx.saved_tensors
-        dh = ops.swiglu_bwd(da.reshape(-1, da.shape[-1]).contiguous(), h2, None)
-        return dh.reshape(ctx.shape)
-
-
 class TimestepEmbedFn(Function):
     """PositionalEncoding(t * time_scale) (PositionalEncoding.py:23-30, diff_model.py:306) -> bf16."""
 
@@ -336,80 +357,6 @@ class TimestepEmbedFn(Function):
         ds = torch.zeros(1, device=de.device, dtype=F32)
         ops.timestep_embed_bwd(de.contiguous(), t, time_scale, denom, ds)
         return None, ds, None
-
-
-class TextNormFn(Function):
-    """sigma * RMSNorm(c) per encoder half (diff_model.py:323-326) -> two bf16 row blocks."""
-
-    @staticmethod
-    def forward(ctx, c, w1, w2, s1, s2, split):
-        c = c.contiguous()
-        o1, o2, rstd = ops.text_norm_fwd(c, w1, w2, s1, s2, split)
-        ctx.save_for_backward(c, rstd, w1, w2, s1, s2)
-        ctx.split = split
-        ctx.set_materialize_grads(False)
-        return o1, o2
-
-    @staticmethod
-    def backward(ctx, d1, d2):
-        c, rstd, w1, w2, s1, s2 = ctx.saved_tensors
-        split, M = ctx.split, c.shape[1]
-        dw1, dw2 = torch.zeros_like(w1), torch.zeros_like(w2)
-        ds1, ds2 = torch.zeros_like(s1), torch.zeros_like(s2)
-        if d1 is not None:
-            ops.text_norm_bwd(d1.contiguous(), c, rstd, w1, s1, dw1, ds1, 0, split)
-        if d2 is not None and M > split:
-            ops.text_norm_bwd(d2.contiguous(), c, rstd, w2, s2, dw2, ds2, split, M - split)
-        return None, dw1, dw2, ds1, ds2, None
-
-
-class ScatterRowsFn(Function):
-    """Places two row blocks ([B*n1, d], [B*n2, d]) into one [B, n1+n2, d] sequence
-    (the torch.cat at diff_model.py:323-326) -- done by the GEMM epilogue's row remap in
-    forward (see TextProjFn); this Function only exists for the standalone concat case."""
-
-    @staticmethod
-    def forward(ctx, a, b, Bn):
-        n1, n2, d = a.shape[0] // Bn, b.shape[0] // Bn, a.shape[1]
-        ctx.dims = (Bn, n1, n2, d)
-        return torch.cat([a.view(Bn, n1, d), b.view(Bn, n2, d)], 1)
-
-    @staticmethod
-    def backward(ctx, g):
-        Bn, n1, n2, d = ctx.dims
-        return (g[:, :n1].reshape(Bn * n1, d), g[:, n1:].reshape(Bn * n2, d), None)
-
-
-class TextProjFn(Function):
-    """c' = cat[c_proj(n1), c_proj2(n2)] along tokens (diff_model.py:323-326): two GEMMs whose
-    epilogues scatter rows straight into the [B, M, d] sequence."""
-
-    @staticmethod
-    def forward(ctx, n1, n2, wb1, wb2, Bn, w1, w2):
-        t1 = n1.shape[0] // Bn
-        t2 = n2.shape[0] // Bn if n2 is not None else 0
-        M, d = t1 + t2, wb1.shape[0]
-        out = torch.empty((Bn * M, d), device=n1.device, dtype=BF16)
-        ops.gemm(n1, wb1, out=out, remap=(t1, M, 0))
-        if t2:
-            ops.gemm(n2, wb2, out=out, remap=(t2, M, t1))
-        ctx.save_for_backward(n1, n2, wb1, wb2)
-        ctx.dims = (Bn, t1, t2, d)
-        return out.view(Bn, M, d)
-
-    @staticmethod
-    def backward(ctx, g):
-        n1, n2, wb1, wb2 = ctx.saved_tensors
-        Bn, t1, t2, d = ctx.dims
-        g1 = g[:, :t1].reshape(Bn * t1, d)
-        dn1 = ops.gemm(g1, wb1, b_major=1)
-        dw1 = ops.gemm(g1, n1, a_major=1, b_major=1, out_dtype=F32)
-        dn2 = dw2 = None
-        if t2:
-            g2 = g[:, t1:].reshape(Bn * t2, d)
-            dn2 = ops.gemm(g2, wb2, b_major=1)
-            dw2 = ops.gemm(g2, n2, a_major=1, b_major=1, out_dtype=F32)
-        return dn1, dn2, None, None, None, dw1, dw2
 
 
 class PatchifyFn(Function):

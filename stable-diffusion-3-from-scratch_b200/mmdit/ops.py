@@ -422,3 +422,17 @@ def gate_residual_fwd(a, gate, resid, rows_per_batch):
                                                   rows_per_batch, gate.stride(0), _s()),
                "mmdit_gate_residual_fwd")
     return out
+
+
+def gate_residual_ln_fwd(a, gate, resid, shift, scale, rows_per_batch):
+    """x' = a * gate[b] + resid and y = LN(x') * (1 + scale[b]) + shift[b] in one pass.
+    Returns (x' bf16 [R,d], y bf16 [R,d], mean fp32 [R], rstd fp32 [R])."""
+    R, d = a.shape
+    assert a.is_contiguous() and resid.is_contiguous() and shift.stride(0) == scale.stride(0)
+    xo, y = torch.empty_like(a), torch.empty_like(a)
+    mean = torch.empty(R, device=a.device, dtype=F32)
+    rstd = torch.empty(R, device=a.device, dtype=F32)
+    _lib.check(_lib.lib().mmdit_gate_residual_ln_fwd(
+        _p(a), _p(gate), _p(resid), _p(shift), _p(scale), _p(xo), _p(y), _p(mean), _p(rstd), R, d,
+        rows_per_batch, gate.stride(0), shift.stride(0), LN_EPS, _s()), "mmdit_gate_residual_ln_fwd")
+    return xo, y, mean, rstd

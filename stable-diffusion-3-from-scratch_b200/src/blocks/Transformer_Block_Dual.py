@@ -13,7 +13,8 @@ import torch
 from torch import nn
 
 from mmdit import ops, streams
-from mmdit.functional import FUSED_QKNORM, GatedLinearFn, LinearFn
+from mmdit import functional as Fn
+from mmdit.functional import FUSED_QKNORM, GatedLinearFn, GatedLinearLNFn, LinearFn
 from mmdit.shadow import packed_weight
 from src.blocks.Attention import Attention
 from src.blocks.MLP import MLP, SwiGLU
@@ -114,18 +115,28 @@ class Transformer_Block_Dual(nn.Module):
             c = self._c_branch(a_c, c, m, B, M)
         return X, c
 
+    def _gated_ln(self, a, lin, gate, resid, shift, scale, rows_per_batch):
+        """(LN-mod(X'), X') with X' = resid + gate * lin(a): the out-projection's gated residual and the
+        LayerNorm-modulate in front of the MLP share one pass over the GEMM output."""
+        if not Fn.FUSED_GATE_LN:
+            return modulate_keep(self._gated(a, lin, gate, resid, rows_per_batch), shift, scale)
+        wb = packed_weight(lin, "w", [lin.weight])
+        bb = None if lin.bias is None else lin.bias.detach()
+        B, T, d = resid.shape
+        y, xo = GatedLinearLNFn.apply(a, wb, bb, gate, resid.reshape(B * T, d), shift, scale, rows_per_batch,
+                                      lin.weight, lin.bias)
+        return y.view(B, T, d), xo.view(B, T, d)
+
     def _x_branch(self, a_x, X, m, B, N):
         """Image stream after the attention: out-projection, gate, MLP, gate."""
-        X = self._gated(a_x, self.attn.out_proj_x, m[4], X, N)
+        xn, X = self._gated_ln(a_x, self.attn.out_proj_x, m[4], X, m[5], m[6], N)
         mx = self._swiglu(self.MLP_x)
-        xn, X = modulate_keep(X, m[5], m[6])
         return self._gated(mx.hidden(xn).reshape(B * N, -1), mx.w3, m[7], X, N)
 
     def _c_branch(self, a_c, c, m, B, M):
         """Text stream after the attention (absent in the last block)."""
-        c = self._gated(a_c, self.attn.out_proj_c, m[8], c, M)
+        cn, c = self._gated_ln(a_c, self.attn.out_proj_c, m[8], c, m[9], m[10], M)
         mc = self._swiglu(self.MLP_c)
-        cn, c = modulate_keep(c, m[9], m[10])
         return self._gated(mc.hidden(cn).reshape(B * M, -1), mc.w3, m[11], c, M)
 
     def _forward_two_streams(self, X, c, m, orig_shape, B, N, M):

@@ -176,6 +176,12 @@ def gate_residual_fwd(a, gate, resid, rows_per_batch):
     return _bf(a.float() * _rows(gate, rows_per_batch) + resid.float())
 
 
+def gate_residual_ln_fwd(a, gate, resid, shift, scale, rows_per_batch):
+    xo = gate_residual_fwd(a, gate, resid, rows_per_batch)
+    y, mean, rstd = ln_modulate_fwd(xo, shift, scale, rows_per_batch)
+    return xo, y, mean, rstd
+
+
 def gate_bwd(dout, a, gate, dgate, dab, rows_per_batch):
     B, d = gate.shape
     da = dout.float() * _rows(gate, rows_per_batch)

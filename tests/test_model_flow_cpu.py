@@ -71,6 +71,15 @@ def test_unfused_swiglu_and_fused_qknorm_paths_agree(cpu_kernels, golden, monkey
     g = golden("cfg1")
     base_model, base_v, base_loss = _run(g["config"], g)
 
+    # gated residual + LayerNorm-modulate as two kernels instead of the fused pass: same function
+    monkeypatch.setattr(functional, "FUSED_GATE_LN", False)
+    m1, v1, loss1 = _run(g["config"], g)
+    assert torch.equal(v1, base_v) and loss1 == base_loss
+    for (k, p), (_, q) in zip(m1.named_parameters(), base_model.named_parameters()):
+        if p.requires_grad:
+            assert torch.equal(p.grad, q.grad), k
+    monkeypatch.setattr(functional, "FUSED_GATE_LN", True)
+
     monkeypatch.setattr(functional, "FUSED_SWIGLU", False)
     m2, v2, loss2 = _run(g["config"], g)
     assert abs(loss2 - base_loss) <= 2e-3

@@ -70,6 +70,8 @@ __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, 
 template <bool PT_TMEM>
 __global__ void __launch_bounds__(BWD_THREADS, 1)
 attn_bwd_kernel(const __grid_constant__ AttnBwdParams p) {
+  // (no early pdl_trigger: dependents are released when this grid exits)
+  pdl_wait();   // programmatic dependent launch: the previous kernel's writes are visible from here
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sK = smem;
   uint8_t* sV = smem + ATT_TILE_BYTES;
@@ -463,6 +465,8 @@ __global__ void __launch_bounds__(256)
 attn_delta_kernel(const bf16* __restrict__ o, const bf16* __restrict__ d_o, float* __restrict__ delta,
                   long long rows, int H, long long ld_o, long long ld_do, int rows_per_sample,
                   int t_off, int T) {
+  // (no early pdl_trigger: dependents are released when this grid exits)
+  pdl_wait();   // programmatic dependent launch: the previous kernel's writes are visible from here
   const long long total = rows * H * 8;
   const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   const bool active = idx < total;
@@ -491,6 +495,8 @@ attn_delta_kernel(const bf16* __restrict__ o, const bf16* __restrict__ d_o, floa
 __global__ void __launch_bounds__(256)
 attn_dq_convert_kernel(const float* __restrict__ acc, bf16* __restrict__ dq, int B, int T, int t_off,
                        int rows_per_sample, int dmodel, long long ld_dq) {
+  // (no early pdl_trigger: dependents are released when this grid exits)
+  pdl_wait();   // programmatic dependent launch: the previous kernel's writes are visible from here
   const int groups = dmodel / 8;
   const long long total = (long long)B * rows_per_sample * groups;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
@@ -567,7 +573,7 @@ extern "C" int mmdit_attn_bwd(const mmdit_attn_args* a, void* stream_) {
     const long long nrows = (long long)a->B * rows[s];
     const long long work = nrows * a->H * 8;
     MMDIT_CARVEOUT(attn_delta_kernel);
-    attn_delta_kernel<<<(unsigned)((work + 255) / 256), 256, 0, stream>>>(
+    launch_k(attn_delta_kernel, dim3((unsigned)((work + 255) / 256)), dim3(256), 0, stream, 
         static_cast<const bf16*>(a->o[s]), static_cast<const bf16*>(a->d_o[s]), a->delta, nrows,
         a->H, a->ld_o[s], a->ld_do[s], rows[s], s == 0 ? 0 : a->N, T);
   }
@@ -593,8 +599,8 @@ extern "C" int mmdit_attn_bwd(const mmdit_attn_args* a, void* stream_) {
   }
   const int nt = (a->N + ATT_TILE - 1) / ATT_TILE + (a->M + ATT_TILE - 1) / ATT_TILE;
   dim3 grid(nt, a->H, a->B);
-  if (pt_tmem) attn_bwd_kernel<true><<<grid, BWD_THREADS, BWD_SMEM, stream>>>(p);
-  else attn_bwd_kernel<false><<<grid, BWD_THREADS, BWD_SMEM, stream>>>(p);
+  if (pt_tmem) launch_k(attn_bwd_kernel<true>, grid, dim3(BWD_THREADS), BWD_SMEM, stream, p);
+  else launch_k(attn_bwd_kernel<false>, grid, dim3(BWD_THREADS), BWD_SMEM, stream, p);
   rc = check_launch("attn_bwd_kernel");
   if (rc) return rc;
   for (int s = 0; s < 2; ++s) {
@@ -603,7 +609,7 @@ extern "C" int mmdit_attn_bwd(const mmdit_attn_args* a, void* stream_) {
     long long blocks = (work + 255) / 256;
     if (blocks > num_sms() * 16LL) blocks = num_sms() * 16LL;
     MMDIT_CARVEOUT(attn_dq_convert_kernel);
-    attn_dq_convert_kernel<<<(unsigned)blocks, 256, 0, stream>>>(
+    launch_k(attn_dq_convert_kernel, dim3((unsigned)blocks), dim3(256), 0, stream, 
         a->dq_acc, static_cast<bf16*>(a->dq[s]), a->B, T, s == 0 ? 0 : a->N, rows[s], dmodel,
         a->ld_dq[s]);
   }

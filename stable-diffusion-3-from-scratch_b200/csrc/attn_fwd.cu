@@ -60,6 +60,8 @@ struct AttnFwdParams {
 
 __global__ void __launch_bounds__(ATT_THREADS, 2)
 attn_fwd_kernel(const __grid_constant__ AttnFwdParams p) {
+  // (no early pdl_trigger: dependents are released when this grid exits)
+  pdl_wait();   // programmatic dependent launch: the previous kernel's writes are visible from here
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sQ = smem;
   uint8_t* sK = smem + ATT_TILE_BYTES;
@@ -441,6 +443,6 @@ extern "C" int mmdit_attn_fwd(const mmdit_attn_args* a, void* stream) {
   }
   const int nt = (a->N + ATT_TILE - 1) / ATT_TILE + (a->M + ATT_TILE - 1) / ATT_TILE;
   dim3 grid(nt, a->H, a->B);
-  attn_fwd_kernel<<<grid, ATT_THREADS, ATT_SMEM, static_cast<cudaStream_t>(stream)>>>(p);
+  launch_k(attn_fwd_kernel, grid, dim3(ATT_THREADS), ATT_SMEM, static_cast<cudaStream_t>(stream), p);
   return check_launch("attn_fwd_kernel");
 }

@@ -125,9 +125,6 @@ attn_fwd2_kernel(const __grid_constant__ AttnFwd2Params p) {
   uint64_t* o_free = bars + 16;   // 256: O of the finished item is in registers
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
 
-  const float bound = *p.logit_bound;
-  if (!(bound >= 0.f && bound <= 24.f)) return;   // the online-softmax kernel handles this launch
-
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ntx = (p.N + F2_TILE - 1) / F2_TILE;
   const int ntc = (p.M + F2_TILE - 1) / F2_TILE;
@@ -167,6 +164,9 @@ attn_fwd2_kernel(const __grid_constant__ AttnFwd2Params p) {
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tm_S = tmem_base, tm_P = tmem_base + 128, tm_O = tmem_base + 192;
+  pdl_wait();   // barrier init and the TMEM allocation overlapped the previous kernel's tail
+  const float bound = *p.logit_bound;
+  const bool usable = bound >= 0.f && bound <= 24.f;   // else: the online-softmax kernel handles this launch
 
   auto decode = [&](int item, int& b, int& h, int& qt) {
     qt = item % nt;
@@ -175,7 +175,9 @@ attn_fwd2_kernel(const __grid_constant__ AttnFwd2Params p) {
     b = bh / p.H;
   };
 
-  if (warp == 0) {
+  if (!usable) {
+    // nothing to do (the TMEM allocation is still released below)
+  } else if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       int n = 0;   // key tiles issued so far (ring position), over all items
@@ -426,6 +428,7 @@ attn_fwd2_kernel(const __grid_constant__ AttnFwd2Params p) {
     }
     if (warp == 2 && lane == 0) tma_wait_group0();   // staging tiles must outlive their stores
   }
+  if (warp >= 2) pdl_trigger();   // late trigger, see gemm_tcgen05.cu
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem_base, 256);
@@ -472,6 +475,6 @@ int launch_attn_fwd2(const mmdit_attn_args* a, cudaStream_t stream) {
     return (int)attr_rc;
   }
   const int grid = p.items < 2 * num_sms() ? p.items : 2 * num_sms();
-  attn_fwd2_kernel<<<grid, F2_THREADS, F2_SMEM, stream>>>(p);
+  launch_k(attn_fwd2_kernel, dim3(grid), dim3(F2_THREADS), F2_SMEM, stream, p);
   return check_launch("attn_fwd2_kernel");
 }

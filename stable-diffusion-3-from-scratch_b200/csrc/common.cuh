@@ -6,6 +6,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
 
 namespace mmdit {
 
@@ -50,8 +51,39 @@ void prefer_max_smem_carveout(const void* kernel);
     (void)once_;                                                                          \
   } while (0)
 
+// ---------------------------------------------------------------- launch ---
+// Programmatic dependent launch: a kernel launched through launch_k() may be scheduled while the
+// previous kernel of its stream is still running (as soon as every CTA of that kernel has executed
+// pdl_trigger() or exited), runs its prologue (barrier init, TMEM allocation, descriptor prefetch)
+// and blocks in pdl_wait() until the previous kernel has completed and its writes are visible.  Every
+// kernel launched this way calls pdl_wait() before its first global-memory access.  Inside a captured
+// CUDA graph the launch becomes a programmatic edge.  MMDIT_PDL=0 turns the attribute off (the device
+// instructions are then no-ops).
+bool pdl_enabled();
+#ifdef __CUDACC__
+template <typename... KArgs, typename... Args>
+inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                     Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);   // errors surface in check_launch()
+}
+#endif
+
 // ---------------------------------------------------------------- device ---
 #ifdef __CUDACC__
+
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));

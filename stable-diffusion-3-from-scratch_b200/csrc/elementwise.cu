@@ -24,6 +24,8 @@ qknorm_rope_fwd_kernel(const bf16* __restrict__ qkv, const float* __restrict__ w
                        const float* __restrict__ wk, const float* __restrict__ rope_cos,
                        const float* __restrict__ rope_sin, bf16* __restrict__ out, long long R,
                        int d, long long ld_in, long long ld_out, int tokens_per_sample, float eps) {
+  // (no early pdl_trigger: dependents are released when this grid exits)
+  pdl_wait();   // programmatic dependent launch: the previous kernel's writes are visible from here
   const int groups = d / 8;
   const long long total = R * groups;
   // total and the grid stride are multiples of 8, so the 8 lanes of a head are
@@ -86,6 +88,8 @@ qknorm_rope_bwd_kernel(const bf16* __restrict__ dqk, const bf16* __restrict__ qk
                        bf16* __restrict__ dqkv, float* __restrict__ dwq, float* __restrict__ dwk,
                        long long R, int d, long long ld_g, long long ld_in, long long ld_dout,
                        int tokens_per_sample, float eps) {
+  // (no early pdl_trigger: dependents are released when this grid exits)
+  pdl_wait();   // programmatic dependent launch: the previous kernel's writes are visible from here
   __shared__ float red[2][64];
   if (threadIdx.x < 128) (&red[0][0])[threadIdx.x] = 0.f;
   __syncthreads();
@@ -193,6 +197,8 @@ qknorm_rope_bwd_kernel(const bf16* __restrict__ dqk, const bf16* __restrict__ qk
 // h12: [R, 2*hid] (x1 = gate half at column 0, x2 at column hid); a = silu(x1)*x2.
 __global__ void __launch_bounds__(256)
 swiglu_fwd_kernel(const bf16* __restrict__ h12, bf16* __restrict__ a, long long R, int hid) {
+  // (no early pdl_trigger: dependents are released when this grid exits)
+  pdl_wait();   // programmatic dependent launch: the previous kernel's writes are visible from here
   const int groups = hid / 8;
   const long long total = R * groups;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
@@ -214,6 +220,8 @@ __global__ void __launch_bounds__(128)
 swiglu_bwd_kernel(const bf16* __restrict__ da, const bf16* __restrict__ h12,
                   bf16* __restrict__ dh12, float* __restrict__ partial, long long R, int hid,
                   int rows_per_block) {
+  // (no early pdl_trigger: dependents are released when this grid exits)
+  pdl_wait();   // programmatic dependent launch: the previous kernel's writes are visible from here
   const int col = (blockIdx.x * 128 + threadIdx.x) * 8;
   if (col >= hid) return;
   const long long r0 = (long long)blockIdx.y * rows_per_block;
@@ -277,6 +285,8 @@ __global__ void __launch_bounds__(256)
 gate_residual_fwd_kernel(const bf16* __restrict__ a, const bf16* __restrict__ gate,
                          const bf16* __restrict__ resid, bf16* __restrict__ out, long long R, int d,
                          long long rows_per_batch, long long ld_gate) {
+  // (no early pdl_trigger: dependents are released when this grid exits)
+  pdl_wait();   // programmatic dependent launch: the previous kernel's writes are visible from here
   const int groups = d / 8;
   const long long total = R * groups;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
@@ -426,6 +436,8 @@ __global__ void cfg_euler_kernel(float* __restrict__ x, const VT* __restrict__ v
 __global__ void __launch_bounds__(128)
 colsum_bf16_kernel(const bf16* __restrict__ in, float* __restrict__ out, long long R, int n,
                    long long ld, int rows_per_block) {
+  // (no early pdl_trigger: dependents are released when this grid exits)
+  pdl_wait();   // programmatic dependent launch: the previous kernel's writes are visible from here
   const int col = (blockIdx.x * 128 + threadIdx.x) * 8;
   if (col >= n) return;
   const long long r0 = (long long)blockIdx.y * rows_per_block;
@@ -446,6 +458,8 @@ colsum_bf16_kernel(const bf16* __restrict__ in, float* __restrict__ out, long lo
 // out[n] += sum_rows in[row, n] (fp32 in), small row counts (per-batch partials).
 __global__ void fold_rows_f32_kernel(const float* __restrict__ in, float* __restrict__ out, int R,
                                      int n, long long ld) {
+  // (no early pdl_trigger: dependents are released when this grid exits)
+  pdl_wait();   // programmatic dependent launch: the previous kernel's writes are visible from here
   // grid.y row groups, each adds its partial column sum with one atomic (few groups -> cheap)
   const int col = blockIdx.x * blockDim.x + threadIdx.x;
   if (col >= n) return;
@@ -464,6 +478,8 @@ __global__ void fold_rows_f32_kernel(const float* __restrict__ in, float* __rest
 }
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ in, bf16* __restrict__ out,
                                      long long n) {
+  // (no early pdl_trigger: dependents are released when this grid exits)
+  pdl_wait();   // programmatic dependent launch: the previous kernel's writes are visible from here
   const long long n8 = n / 8;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8;
        i += (long long)gridDim.x * blockDim.x) {
@@ -481,6 +497,8 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ in, bf16* __restr
 __global__ void __launch_bounds__(256)
 fold_slices_kernel(const float* __restrict__ ws, float* __restrict__ out, long long n, int slices,
                    long long stride, int accumulate) {
+  // (no early pdl_trigger: dependents are released when this grid exits)
+  pdl_wait();   // programmatic dependent launch: the previous kernel's writes are visible from here
   const long long n4 = n / 4;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4;
        i += (long long)gridDim.x * blockDim.x) {
@@ -532,7 +550,7 @@ int mmdit_qknorm_rope_fwd(const void* qkv, const float* wq, const float* wk, con
                 MMDIT_ERR_ARG, "qknorm_rope_fwd: bad arguments (head_dim is fixed at 64)");
   const long long work = rows * (long long)(d / 8);
   MMDIT_CARVEOUT(qknorm_rope_fwd_kernel);
-  qknorm_rope_fwd_kernel<<<grid_for(work, 256), 256, 0, (cudaStream_t)stream>>>(
+  launch_k(qknorm_rope_fwd_kernel, dim3(grid_for(work, 256)), dim3(256), 0, (cudaStream_t)stream, 
       (const bf16*)qkv, wq, wk, rope_cos, rope_sin, (bf16*)out, rows, d, ld_in, ld_out,
       tokens_per_sample, eps);
   return check_launch("qknorm_rope_fwd_kernel");
@@ -550,7 +568,7 @@ int mmdit_qknorm_rope_bwd(const void* dqk, const void* qkv, const float* wq, con
   const unsigned cap = (unsigned)num_sms() * 4;  // fewer, longer-lived blocks: fewer atomics
   if (grid > cap) grid = cap;
   MMDIT_CARVEOUT(qknorm_rope_bwd_kernel);
-  qknorm_rope_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
+  launch_k(qknorm_rope_bwd_kernel, grid, dim3(256), 0, (cudaStream_t)stream, 
       (const bf16*)dqk, (const bf16*)qkv, wq, wk, rope_cos, rope_sin, (bf16*)dqkv, dwq, dwk, rows,
       d, ld_g, ld_in, ld_dout, tokens_per_sample, eps);
   return check_launch("qknorm_rope_bwd_kernel");
@@ -564,7 +582,7 @@ int mmdit_gate_residual_fwd(const void* a, const void* gate, const void* resid, 
                 MMDIT_ERR_ARG, "gate_residual_fwd: bad arguments");
   const long long work = rows * (long long)(d / 8);
   MMDIT_CARVEOUT(gate_residual_fwd_kernel);
-  gate_residual_fwd_kernel<<<grid_for(work, 256), 256, 0, (cudaStream_t)stream>>>(
+  launch_k(gate_residual_fwd_kernel, dim3(grid_for(work, 256)), dim3(256), 0, (cudaStream_t)stream, 
       (const bf16*)a, (const bf16*)gate, (const bf16*)resid, (bf16*)out, rows, d, rows_per_batch,
       ld_gate);
   return check_launch("gate_residual_fwd_kernel");
@@ -582,7 +600,7 @@ int mmdit_swiglu_fwd(const void* h12, void* a, int64_t rows, int32_t hidden, voi
                 "swiglu_fwd: bad arguments");
   const long long work = rows * (long long)(hidden / 8);
   MMDIT_CARVEOUT(swiglu_fwd_kernel);
-  swiglu_fwd_kernel<<<grid_for(work, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)h12,
+  launch_k(swiglu_fwd_kernel, dim3(grid_for(work, 256)), dim3(256), 0, (cudaStream_t)stream, (const bf16*)h12,
                                                                           (bf16*)a, rows, hidden);
   return check_launch("swiglu_fwd_kernel");
 }
@@ -600,11 +618,11 @@ int mmdit_swiglu_bwd(const void* da, const void* h12, void* dh12, float* db12, f
   const int nrb = (int)((rows + rpb - 1) / rpb);
   dim3 grid((unsigned)((hidden / 8 + 127) / 128), (unsigned)nrb);
   MMDIT_CARVEOUT(swiglu_bwd_kernel);
-  swiglu_bwd_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>((const bf16*)da, (const bf16*)h12,
+  launch_k(swiglu_bwd_kernel, grid, dim3(128), 0, (cudaStream_t)stream, (const bf16*)da, (const bf16*)h12,
                                                            (bf16*)dh12, db12 ? workspace : nullptr,
                                                            rows, hidden, rpb);
   if (db12)
-    fold_rows_f32_kernel<<<dim3((2 * hidden + 255) / 256, nrb >= 32 ? 16 : 1), 256, 0, (cudaStream_t)stream>>>(
+    launch_k(fold_rows_f32_kernel, dim3((2 * hidden + 255) / 256, nrb >= 32 ? 16 : 1), dim3(256), 0, (cudaStream_t)stream, 
         workspace, db12, nrb, 2 * hidden, 2 * (long long)hidden);
   return check_launch("swiglu_bwd_kernel", db12 ? 2 : 1);
 }
@@ -728,14 +746,14 @@ int mmdit_colsum_bf16(const void* in, float* out, int64_t rows, int32_t n, int64
   int rpb = 64;
   if (rows > 65535LL * rpb) rpb = (int)((rows + 65534) / 65535);
   dim3 grid((unsigned)((n / 8 + 127) / 128), (unsigned)((rows + rpb - 1) / rpb));
-  colsum_bf16_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>((const bf16*)in, out, rows, n, ld, rpb);
+  launch_k(colsum_bf16_kernel, grid, dim3(128), 0, (cudaStream_t)stream, (const bf16*)in, out, rows, n, ld, rpb);
   return check_launch("colsum_bf16_kernel");
 }
 
 int mmdit_fold_rows_f32(const float* in, float* out, int32_t rows, int32_t n, int64_t ld,
                         void* stream) {
   MMDIT_REQUIRE(in && out && rows > 0 && n > 0, MMDIT_ERR_ARG, "fold_rows_f32: bad arguments");
-  fold_rows_f32_kernel<<<dim3((n + 255) / 256, rows >= 32 ? 16 : 1), 256, 0, (cudaStream_t)stream>>>(in, out, rows, n, ld);
+  launch_k(fold_rows_f32_kernel, dim3((n + 255) / 256, rows >= 32 ? 16 : 1), dim3(256), 0, (cudaStream_t)stream, in, out, rows, n, ld);
   return check_launch("fold_rows_f32_kernel");
 }
 
@@ -745,7 +763,7 @@ int mmdit_fold_slices_f32(const float* ws, float* out, int64_t n, int32_t slices
                     ((uintptr_t)ws & 15) == 0 && ((uintptr_t)out & 15) == 0,
                 MMDIT_ERR_ARG, "fold_slices_f32: bad arguments");
   MMDIT_CARVEOUT(fold_slices_kernel);
-  fold_slices_kernel<<<grid_for(n / 4, 256), 256, 0, (cudaStream_t)stream>>>(ws, out, n, slices, stride,
+  launch_k(fold_slices_kernel, dim3(grid_for(n / 4, 256)), dim3(256), 0, (cudaStream_t)stream, ws, out, n, slices, stride,
                                                                              accumulate);
   return check_launch("fold_slices_kernel");
 }
@@ -753,7 +771,7 @@ int mmdit_fold_slices_f32(const float* ws, float* out, int64_t n, int32_t slices
 int mmdit_cast_f32_bf16(const float* in, void* out, int64_t n, void* stream) {
   MMDIT_REQUIRE(in && out && n > 0 && ((uintptr_t)in & 15) == 0 && ((uintptr_t)out & 15) == 0,
                 MMDIT_ERR_ARG, "cast_f32_bf16: bad arguments (16-byte aligned buffers)");
-  cast_f32_bf16_kernel<<<grid_for(n / 8 + 1, 256), 256, 0, (cudaStream_t)stream>>>(in, (bf16*)out, n);
+  launch_k(cast_f32_bf16_kernel, dim3(grid_for(n / 8 + 1, 256)), dim3(256), 0, (cudaStream_t)stream, in, (bf16*)out, n);
   return check_launch("cast_f32_bf16_kernel");
 }
 

@@ -24,6 +24,8 @@ constexpr int OPT_CHUNK = 16384;  // elements per block
 __global__ void __launch_bounds__(OPT_THREADS)
 grad_sumsq_kernel(const ParamDesc* __restrict__ table, const int2* __restrict__ chunks,
                   float* __restrict__ state /* [0]=sumsq */) {
+  // (no early pdl_trigger: dependents are released when this grid exits)
+  pdl_wait();   // programmatic dependent launch: the previous kernel's writes are visible from here
   __shared__ float red[OPT_THREADS / 32];
   const int2 w = chunks[blockIdx.x];
   const ParamDesc d = table[w.x];
@@ -55,6 +57,8 @@ __global__ void __launch_bounds__(OPT_THREADS)
 adamw_kernel(const ParamDesc* __restrict__ table, const int2* __restrict__ chunks,
              const float* __restrict__ state /* [0]=sumsq [1]=step (already incremented) [2]=lr */,
              float lr_arg, float beta1, float beta2, float eps, float wd, float max_norm) {
+  // (no early pdl_trigger: dependents are released when this grid exits)
+  pdl_wait();   // programmatic dependent launch: the previous kernel's writes are visible from here
   // lr < 0: the learning rate is the device-resident state[2] (a scheduler rewrites it between
   // replays of a captured step; by-value arguments are frozen into a CUDA graph)
   const float lr = lr_arg < 0.f ? state[2] : lr_arg;
@@ -113,6 +117,8 @@ adamw_kernel(const ParamDesc* __restrict__ table, const int2* __restrict__ chunk
 }
 
 __global__ void opt_begin_kernel(float* state) {
+  // (no early pdl_trigger: dependents are released when this grid exits)
+  pdl_wait();   // programmatic dependent launch: the previous kernel's writes are visible from here
   state[0] = 0.f;     // sum of squares
   state[1] += 1.f;    // step count
 }
@@ -127,10 +133,10 @@ extern "C" int mmdit_adamw_step(const void* table, const void* chunks, int32_t n
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   MMDIT_REQUIRE(table && chunks && state && n_chunks > 0, MMDIT_ERR_ARG, "adamw_step: bad arguments");
   static_assert(sizeof(ParamDesc) == sizeof(mmdit_param_desc), "param desc layout");
-  opt_begin_kernel<<<1, 1, 0, stream>>>(state);
-  grad_sumsq_kernel<<<n_chunks, OPT_THREADS, 0, stream>>>(static_cast<const ParamDesc*>(table),
+  launch_k(opt_begin_kernel, dim3(1), dim3(1), 0, stream, state);
+  launch_k(grad_sumsq_kernel, dim3(n_chunks), dim3(OPT_THREADS), 0, stream, static_cast<const ParamDesc*>(table),
                                                           static_cast<const int2*>(chunks), state);
-  adamw_kernel<<<n_chunks, OPT_THREADS, 0, stream>>>(static_cast<const ParamDesc*>(table),
+  launch_k(adamw_kernel, dim3(n_chunks), dim3(OPT_THREADS), 0, stream, static_cast<const ParamDesc*>(table),
                                                      static_cast<const int2*>(chunks), state, lr, beta1,
                                                      beta2, eps, weight_decay, max_norm);
   return check_launch("adamw_kernel", 3);

@@ -51,6 +51,8 @@ __device__ __forceinline__ void block_fold_partials(float* red, const float (&a0
 __global__ void fold_batch_partials_kernel(const float* __restrict__ partial, void* __restrict__ out0,
                                            void* __restrict__ out1, int d, int blocks_per_batch,
                                            long long ld0, long long ld1, int out0_bf16, int out1_bf16) {
+  // (no early pdl_trigger: dependents are released when this grid exits)
+  pdl_wait();   // programmatic dependent launch: the previous kernel's writes are visible from here
   const int i = blockIdx.x * blockDim.x + threadIdx.x;  // 0 .. 2d
   if (i >= 2 * d) return;
   const long long b = blockIdx.y;
@@ -88,6 +90,8 @@ ln_mod_fwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ shift,
                   const bf16* __restrict__ scale, bf16* __restrict__ y, float* __restrict__ mean_out,
                   float* __restrict__ rstd_out, long long R, int d, long long rows_per_batch,
                   long long ld_mod, float eps) {
+  // (no early pdl_trigger: dependents are released when this grid exits)
+  pdl_wait();   // programmatic dependent launch: the previous kernel's writes are visible from here
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * ROW_WARPS + warp;
   if (row >= R) return;
@@ -148,6 +152,8 @@ gate_res_ln_fwd_kernel(const bf16* __restrict__ a, const bf16* __restrict__ gate
                        const bf16* __restrict__ scale, bf16* __restrict__ xo, bf16* __restrict__ y,
                        float* __restrict__ mean_out, float* __restrict__ rstd_out, long long R, int d,
                        long long rows_per_batch, long long ld_gate, long long ld_mod, float eps) {
+  // (no early pdl_trigger: dependents are released when this grid exits)
+  pdl_wait();   // programmatic dependent launch: the previous kernel's writes are visible from here
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * ROW_WARPS + warp;
   if (row >= R) return;
@@ -219,6 +225,8 @@ ln_mod_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
                   bf16* __restrict__ dx, float* __restrict__ partial,
                   int d, long long rows_per_batch, long long ld_mod,
                   int rows_per_block, int blocks_per_batch) {
+  // (no early pdl_trigger: dependents are released when this grid exits)
+  pdl_wait();   // programmatic dependent launch: the previous kernel's writes are visible from here
   extern __shared__ float red[];  // [BWD_WARPS][2][d]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long b = blockIdx.x / blocks_per_batch;
@@ -295,6 +303,8 @@ gate_bwd_kernel(const bf16* __restrict__ dout, const bf16* __restrict__ a,
                 const bf16* __restrict__ gate, bf16* __restrict__ da, float* __restrict__ partial,
                 int d, long long rows_per_batch, long long ld_gate, int rows_per_block,
                 int blocks_per_batch) {
+  // (no early pdl_trigger: dependents are released when this grid exits)
+  pdl_wait();   // programmatic dependent launch: the previous kernel's writes are visible from here
   extern __shared__ float red[];  // [BWD_WARPS][2][d]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long b = blockIdx.x / blocks_per_batch;
@@ -480,7 +490,7 @@ int mmdit_ln_modulate_fwd(const void* x, const void* shift, const void* scale, v
   MMDIT_REQUIRE(x && shift && scale && y && rows > 0 && d > 0 && d % 8 == 0 && rows_per_batch > 0,
                 MMDIT_ERR_ARG, "ln_modulate_fwd: bad arguments (d must be a multiple of 8)");
   const unsigned grid = (unsigned)((rows + ROW_WARPS - 1) / ROW_WARPS);
-  DISPATCH_NC(d, MMDIT_CARVEOUT(ln_mod_fwd_kernel<NC>); (ln_mod_fwd_kernel<NC><<<grid, ROW_THREADS, 0, (cudaStream_t)stream>>>(
+  DISPATCH_NC(d, MMDIT_CARVEOUT(ln_mod_fwd_kernel<NC>); (launch_k(ln_mod_fwd_kernel<NC>, grid, dim3(ROW_THREADS), 0, (cudaStream_t)stream, 
                      (const bf16*)x, (const bf16*)shift, (const bf16*)scale, (bf16*)y, mean, rstd,
                      rows, d, rows_per_batch, ld_mod, eps)));
   return check_launch("ln_mod_fwd_kernel");
@@ -494,7 +504,7 @@ int mmdit_gate_residual_ln_fwd(const void* a, const void* gate, const void* resi
                     rows_per_batch > 0 && ld_gate % 8 == 0 && ld_mod % 8 == 0,
                 MMDIT_ERR_ARG, "gate_residual_ln_fwd: bad arguments (d, ld_gate, ld_mod must be multiples of 8)");
   const unsigned grid = (unsigned)((rows + ROW_WARPS - 1) / ROW_WARPS);
-  DISPATCH_NC(d, MMDIT_CARVEOUT(gate_res_ln_fwd_kernel<NC>); (gate_res_ln_fwd_kernel<NC><<<grid, ROW_THREADS, 0, (cudaStream_t)stream>>>(
+  DISPATCH_NC(d, MMDIT_CARVEOUT(gate_res_ln_fwd_kernel<NC>); (launch_k(gate_res_ln_fwd_kernel<NC>, grid, dim3(ROW_THREADS), 0, (cudaStream_t)stream, 
                      (const bf16*)a, (const bf16*)gate, (const bf16*)resid, (const bf16*)shift,
                      (const bf16*)scale, (bf16*)x_out, (bf16*)y, mean, rstd, rows, d, rows_per_batch,
                      ld_gate, ld_mod, eps)));
@@ -520,12 +530,12 @@ int mmdit_ln_modulate_bwd(const void* dy, const void* x, const float* mean, cons
   const unsigned grid = (unsigned)(nb * bpb);
   const size_t smem = (size_t)BWD_WARPS * 2 * d * sizeof(float);
   MMDIT_REQUIRE(smem <= 48 * 1024, MMDIT_ERR_UNSUPPORTED, "ln_modulate_bwd: d=%d too wide", d);
-  DISPATCH_NC(d, MMDIT_CARVEOUT(ln_mod_bwd_kernel<NC>); (ln_mod_bwd_kernel<NC><<<grid, BWD_THREADS, smem, (cudaStream_t)stream>>>(
+  DISPATCH_NC(d, MMDIT_CARVEOUT(ln_mod_bwd_kernel<NC>); (launch_k(ln_mod_bwd_kernel<NC>, grid, dim3(BWD_THREADS), smem, (cudaStream_t)stream, 
                      (const bf16*)dy, (const bf16*)x, mean, rstd, (const bf16*)scale,
                      (const bf16*)dres, (bf16*)dx, workspace, d, rows_per_batch, ld_mod, rpb, bpb)));
   dim3 g2((2 * d + 255) / 256, nb);
   MMDIT_CARVEOUT(fold_batch_partials_kernel);
-  fold_batch_partials_kernel<<<g2, 256, 0, (cudaStream_t)stream>>>(workspace, dshift, dscale, d, bpb,
+  launch_k(fold_batch_partials_kernel, g2, dim3(256), 0, (cudaStream_t)stream, workspace, dshift, dscale, d, bpb,
                                                                   ld_dmod, ld_dmod, dmod_bf16, dmod_bf16);
   return check_launch("ln_mod_bwd_kernel", 2);
 }
@@ -543,11 +553,11 @@ int mmdit_gate_bwd(const void* dout, const void* a, const void* gate, void* da, 
   const unsigned grid = (unsigned)(nb * bpb);
   const size_t smem = (size_t)BWD_WARPS * 2 * d * sizeof(float);
   MMDIT_REQUIRE(smem <= 48 * 1024, MMDIT_ERR_UNSUPPORTED, "gate_bwd: d=%d too wide", d);
-  DISPATCH_NC(d, MMDIT_CARVEOUT(gate_bwd_kernel<NC>); (gate_bwd_kernel<NC><<<grid, BWD_THREADS, smem, (cudaStream_t)stream>>>(
+  DISPATCH_NC(d, MMDIT_CARVEOUT(gate_bwd_kernel<NC>); (launch_k(gate_bwd_kernel<NC>, grid, dim3(BWD_THREADS), smem, (cudaStream_t)stream, 
                      (const bf16*)dout, (const bf16*)a, (const bf16*)gate, (bf16*)da, workspace, d,
                      rows_per_batch, ld_gate, rpb, bpb)));
   dim3 g2((2 * d + 255) / 256, nb);
-  fold_batch_partials_kernel<<<g2, 256, 0, (cudaStream_t)stream>>>(workspace, dgate, dab, d, bpb,
+  launch_k(fold_batch_partials_kernel, g2, dim3(256), 0, (cudaStream_t)stream, workspace, dgate, dab, d, bpb,
                                                                   ld_dgate, ld_dab, dgate_bf16, 0);
   return check_launch("gate_bwd_kernel", 2);
 }

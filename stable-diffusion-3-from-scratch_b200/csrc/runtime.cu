@@ -83,6 +83,14 @@ int encode_tmap(CUtensorMap* map, const void* base, int rank, const uint64_t* di
   return MMDIT_OK;
 }
 
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("MMDIT_PDL");
+    return e ? atoi(e) != 0 : true;
+  }();
+  return on;
+}
+
 void prefer_max_smem_carveout(const void* kernel) {
   static int on = -1;
   if (on < 0) {

@@ -122,10 +122,10 @@ typedef struct mmdit_attn_args {
   float scale;
   /* backward only */
   const void* d_o[2]; int64_t ld_do[2];
-  void* dq[2]; void* dk[2]; void* dv[2];
+  void* dq[2]; void* dk[2]; void* dv[2];   /* dq[s] may be NULL: dq then stays in dq_acc (fp32) for the caller */
   int64_t ld_dq[2], ld_dk[2], ld_dv[2];
   float* delta;          /* workspace */
-  float* dq_acc;         /* workspace */
+  float* dq_acc;         /* workspace; holds dq (fp32, joint layout) on return */
   /* forward only, optional: device scalar holding an upper bound of |scale * q.k| (see
    * mmdit_qk_logit_bound).  When present and <= 24 the softmax runs in one pass against this
    * fixed reference (no running maximum, no rescaling); otherwise the online-softmax path runs. */
@@ -199,6 +199,15 @@ int mmdit_qknorm_rope_bwd(const void* dqk, const void* qkv, const float* wq, con
                           const float* rope_cos, const float* rope_sin, void* dqkv, float* dwq,
                           float* dwk, int64_t rows, int32_t d, int64_t ld_g, int64_t ld_in,
                           int64_t ld_dout, int32_t tokens_per_sample, float eps, void* stream);
+/* Same, with the q half of the incoming gradient read from the attention backward's fp32 accumulator
+ * (mmdit_attn_args.dq_acc, [B, acc_tokens, d]; this stream's rows start at acc_tok_off inside every sample)
+ * and rounded to bf16 on the fly: call mmdit_attn_bwd with dq[s] = NULL and no bf16 copy of dq is ever
+ * written.  Only the k half (columns d .. 2d) of dqk is read. */
+int mmdit_qknorm_rope_bwd_acc(const float* dq_acc, int32_t acc_tokens, int32_t acc_tok_off, const void* dqk,
+                              const void* qkv, const float* wq, const float* wk, const float* rope_cos,
+                              const float* rope_sin, void* dqkv, float* dwq, float* dwk, int64_t rows,
+                              int32_t d, int64_t ld_g, int64_t ld_in, int64_t ld_dout,
+                              int32_t tokens_per_sample, float eps, void* stream);
 
 /* SwiGLU activation, xformers semantics (MLP.py:19,32): h12 = [x1 | x2], a = silu(x1) * x2.
  * bwd writes dh12 and adds the column sums to db12 [2*hidden] (may be NULL; else needs workspace). */

@@ -542,8 +542,7 @@ extern "C" int mmdit_attn_bwd(const mmdit_attn_args* a, void* stream_) {
   }
   for (int s = 0; s < 2; ++s) {
     if (rows[s] == 0) continue;
-    MMDIT_REQUIRE(a->q[s] && a->k[s] && a->v[s] && a->o[s] && a->d_o[s] && a->dq[s] && a->dk[s] &&
-                      a->dv[s],
+    MMDIT_REQUIRE(a->q[s] && a->k[s] && a->v[s] && a->o[s] && a->d_o[s] && a->dk[s] && a->dv[s],
                   MMDIT_ERR_ARG, "attn_bwd: null pointer in stream %d", s);
     MMDIT_REQUIRE(a->ld_q[s] % 8 == 0 && a->ld_k[s] % 8 == 0 && a->ld_v[s] % 8 == 0 &&
                       a->ld_o[s] % 8 == 0 && a->ld_do[s] % 8 == 0 && a->ld_dq[s] % 8 == 0 &&
@@ -603,8 +602,11 @@ extern "C" int mmdit_attn_bwd(const mmdit_attn_args* a, void* stream_) {
   else launch_k(attn_bwd_kernel<false>, grid, dim3(BWD_THREADS), BWD_SMEM, stream, p);
   rc = check_launch("attn_bwd_kernel");
   if (rc) return rc;
+  int converts = 0;
   for (int s = 0; s < 2; ++s) {
-    if (rows[s] == 0) continue;
+    // dq[s] == NULL: the caller consumes the fp32 accumulator dq_acc itself (mmdit_qknorm_rope_bwd_acc)
+    if (rows[s] == 0 || !a->dq[s]) continue;
+    ++converts;
     const long long work = (long long)a->B * rows[s] * (dmodel / 8);
     long long blocks = (work + 255) / 256;
     if (blocks > num_sms() * 16LL) blocks = num_sms() * 16LL;
@@ -613,5 +615,5 @@ extern "C" int mmdit_attn_bwd(const mmdit_attn_args* a, void* stream_) {
         a->dq_acc, static_cast<bf16*>(a->dq[s]), a->B, T, s == 0 ? 0 : a->N, rows[s], dmodel,
         a->ld_dq[s]);
   }
-  return check_launch("attn_dq_convert_kernel", a->M > 0 ? 2 : 1);
+  return converts ? check_launch("attn_dq_convert_kernel", converts) : 0;
 }

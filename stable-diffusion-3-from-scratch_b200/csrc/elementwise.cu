@@ -81,8 +81,14 @@ qknorm_rope_fwd_kernel(const bf16* __restrict__ qkv, const float* __restrict__ w
 // backward: dqk = grad wrt the normalised/rotated q,k ([R, ld_g], q at 0, k at d);
 // raw qkv as in forward; writes grad wrt raw q,k into dqkv ([R, ld_dout], q at 0, k at d)
 // and accumulates dwq/dwk (64 floats each, fp32 atomics).
+// DQ_F32: the q half of the incoming gradient is read straight from the attention backward's fp32
+// accumulator dq_acc [B, acc_tokens, d] (rows acc_tok_off .. of every sample belong to this stream)
+// instead of a bf16 copy: the separate convert pass (write + re-read of a [R, d] bf16 tensor and one
+// launch per stream) disappears; the value is rounded to bf16 first, exactly as the copy was.
+template <bool DQ_F32>
 __global__ void __launch_bounds__(256)
-qknorm_rope_bwd_kernel(const bf16* __restrict__ dqk, const bf16* __restrict__ qkv,
+qknorm_rope_bwd_kernel(const float* __restrict__ dq_acc, int acc_tokens, int acc_tok_off,
+                       const bf16* __restrict__ dqk, const bf16* __restrict__ qkv,
                        const float* __restrict__ wq, const float* __restrict__ wk,
                        const float* __restrict__ rope_cos, const float* __restrict__ rope_sin,
                        bf16* __restrict__ dqkv, float* __restrict__ dwq, float* __restrict__ dwk,
@@ -113,7 +119,16 @@ qknorm_rope_bwd_kernel(const bf16* __restrict__ dqk, const bf16* __restrict__ qk
     if (active) {
       load8(qkv + row * ld_in + col, q);
       load8(qkv + row * ld_in + d + col, k);
-      load8(dqk + row * ld_g + col, gq);
+      if constexpr (DQ_F32) {
+        const long long arow = (row / tokens_per_sample) * acc_tokens + acc_tok_off + row % tokens_per_sample;
+        const float4 a0 = *reinterpret_cast<const float4*>(dq_acc + arow * d + col);
+        const float4 a1 = *reinterpret_cast<const float4*>(dq_acc + arow * d + col + 4);
+        const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) gq[j] = __bfloat162float(__float2bfloat16(av[j]));
+      } else {
+        load8(dqk + row * ld_g + col, gq);
+      }
       load8(dqk + row * ld_g + d + col, gk);
     } else {
 #pragma unroll
@@ -567,11 +582,32 @@ int mmdit_qknorm_rope_bwd(const void* dqk, const void* qkv, const float* wq, con
   unsigned grid = grid_for(work, 256);
   const unsigned cap = (unsigned)num_sms() * 4;  // fewer, longer-lived blocks: fewer atomics
   if (grid > cap) grid = cap;
-  MMDIT_CARVEOUT(qknorm_rope_bwd_kernel);
-  launch_k(qknorm_rope_bwd_kernel, grid, dim3(256), 0, (cudaStream_t)stream, 
+  MMDIT_CARVEOUT(qknorm_rope_bwd_kernel<false>);
+  launch_k(qknorm_rope_bwd_kernel<false>, grid, dim3(256), 0, (cudaStream_t)stream, (const float*)nullptr, 0, 0,
       (const bf16*)dqk, (const bf16*)qkv, wq, wk, rope_cos, rope_sin, (bf16*)dqkv, dwq, dwk, rows,
       d, ld_g, ld_in, ld_dout, tokens_per_sample, eps);
   return check_launch("qknorm_rope_bwd_kernel");
+}
+
+int mmdit_qknorm_rope_bwd_acc(const float* dq_acc, int32_t acc_tokens, int32_t acc_tok_off, const void* dqk,
+                              const void* qkv, const float* wq, const float* wk, const float* rope_cos,
+                              const float* rope_sin, void* dqkv, float* dwq, float* dwk, int64_t rows,
+                              int32_t d, int64_t ld_g, int64_t ld_in, int64_t ld_dout,
+                              int32_t tokens_per_sample, float eps, void* stream) {
+  MMDIT_REQUIRE(dq_acc && dqk && qkv && wq && wk && dqkv && dwq && dwk && rows > 0 && d % 64 == 0 &&
+                    ld_g % 8 == 0 && ld_in % 8 == 0 && ld_dout % 8 == 0 && tokens_per_sample > 0 &&
+                    acc_tok_off >= 0 && acc_tok_off + tokens_per_sample <= acc_tokens &&
+                    rows % tokens_per_sample == 0,
+                MMDIT_ERR_ARG, "qknorm_rope_bwd_acc: bad arguments");
+  const long long work = rows * (long long)(d / 8);
+  unsigned grid = grid_for(work, 256);
+  const unsigned cap = (unsigned)num_sms() * 4;  // fewer, longer-lived blocks: fewer atomics
+  if (grid > cap) grid = cap;
+  MMDIT_CARVEOUT(qknorm_rope_bwd_kernel<true>);
+  launch_k(qknorm_rope_bwd_kernel<true>, grid, dim3(256), 0, (cudaStream_t)stream, dq_acc, (int)acc_tokens,
+      (int)acc_tok_off, (const bf16*)dqk, (const bf16*)qkv, wq, wk, rope_cos, rope_sin, (bf16*)dqkv, dwq, dwk, rows,
+      d, ld_g, ld_in, ld_dout, tokens_per_sample, eps);
+  return check_launch("qknorm_rope_bwd_kernel<acc>");
 }
 
 int mmdit_gate_residual_fwd(const void* a, const void* gate, const void* resid, void* out,

@@ -23,6 +23,8 @@ SIGNATURES = {
     "mmdit_qknorm_rope_fwd": [vp, vp, vp, vp, vp, vp, i64, i32, i64, i64, i32, f32, vp],
     "mmdit_qk_logit_bound": [vp, vp, vp, vp, f32, vp, vp],
     "mmdit_qknorm_rope_bwd": [vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, i64, i64, i64, i32, f32, vp],
+    "mmdit_qknorm_rope_bwd_acc": [vp, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, i64, i64, i64, i32,
+                                  f32, vp],
     "mmdit_swiglu_fwd": [vp, vp, i64, i32, vp],
     "mmdit_swiglu_bwd": [vp, vp, vp, vp, vp, i64, i32, vp],
     "mmdit_timestep_embed_fwd": [vp, vp, vp, vp, i32, i32, vp],

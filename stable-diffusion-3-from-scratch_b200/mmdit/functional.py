@@ -273,14 +273,16 @@ class JointAttentionFn(Function):
         do_c = torch.zeros_like(o_c) if do_c is None else do_c.contiguous()
         dqkv_x, dqkv_c = torch.empty_like(qkv_x), torch.empty_like(qkv_c)
         dqk_x, dqk_c = torch.empty_like(qk_x), torch.empty_like(qk_c)
-        ops.attn_bwd((qk_x[:, :d], qk_c[:, :d]), (qk_x[:, d:], qk_c[:, d:]),
-                     (qkv_x[:, 2 * d:], qkv_c[:, 2 * d:]), (o_x, o_c), lse, (do_x, do_c),
-                     (dqk_x[:, :d], dqk_c[:, :d]), (dqk_x[:, d:], dqk_c[:, d:]),
-                     (dqkv_x[:, 2 * d:], dqkv_c[:, 2 * d:]), Bn, H, N, M, 0.125)
+        # dq stays in the attention backward's fp32 accumulator: the QK-norm backward reads it from there
+        # (no bf16 convert pass); only the k halves of dqk_x / dqk_c are ever written
+        dq_acc = ops.attn_bwd((qk_x[:, :d], qk_c[:, :d]), (qk_x[:, d:], qk_c[:, d:]),
+                              (qkv_x[:, 2 * d:], qkv_c[:, 2 * d:]), (o_x, o_c), lse, (do_x, do_c),
+                              None, (dqk_x[:, d:], dqk_c[:, d:]),
+                              (dqkv_x[:, 2 * d:], dqkv_c[:, 2 * d:]), Bn, H, N, M, 0.125)
         dw = torch.zeros((4, 64), device=qkv_x.device, dtype=F32)
         rope = (rope_cos, rope_sin) if rope_cos is not None else None
-        ops.qknorm_rope_bwd(dqk_x, qkv_x, wq_x, wk_x, rope, dqkv_x, dw[0], dw[1], d, N)
-        ops.qknorm_rope_bwd(dqk_c, qkv_c, wq_c, wk_c, None, dqkv_c, dw[2], dw[3], d, M)
+        ops.qknorm_rope_bwd(dqk_x, qkv_x, wq_x, wk_x, rope, dqkv_x, dw[0], dw[1], d, N, dq_acc=dq_acc, acc_off=0)
+        ops.qknorm_rope_bwd(dqk_c, qkv_c, wq_c, wk_c, None, dqkv_c, dw[2], dw[3], d, M, dq_acc=dq_acc, acc_off=N)
         return dqkv_x, dqkv_c, dw[0], dw[1], dw[2], dw[3], None, None, None, None, None, None
 
 

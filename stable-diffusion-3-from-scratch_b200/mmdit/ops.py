@@ -192,7 +192,9 @@ def attn_fwd(q, k, v, B, H, N, M, scale, logit_bound=None):
 
 
 def attn_bwd(q, k, v, o, lse, d_o, dq, dk, dv, B, H, N, M, scale):
-    """Writes dq/dk/dv (pairs of [B*rows, H*64] bf16 views) for the joint attention."""
+    """Writes dq/dk/dv (pairs of [B*rows, H*64] bf16 views) for the joint attention.
+    dq=None: no bf16 copy of dq is written; the fp32 accumulator [B, N+M, H*64] (image rows first in
+    every sample) is returned for qknorm_rope_bwd(..., dq_acc=...) to consume."""
     _need_cuda(q[0])
     dev = q[0].device
     T = N + M
@@ -204,12 +206,14 @@ def attn_bwd(q, k, v, o, lse, d_o, dq, dk, dv, B, H, N, M, scale):
     _fill_streams(a, "v", "ld_v", v)
     _fill_streams(a, "o", "ld_o", o)
     _fill_streams(a, "d_o", "ld_do", d_o)
-    _fill_streams(a, "dq", "ld_dq", dq)
+    if dq is not None:
+        _fill_streams(a, "dq", "ld_dq", dq)
     _fill_streams(a, "dk", "ld_dk", dk)
     _fill_streams(a, "dv", "ld_dv", dv)
     a.lse, a.delta, a.dq_acc = lse.data_ptr(), delta.data_ptr(), dq_acc.data_ptr()
     a.B, a.H, a.N, a.M, a.head_dim, a.scale = B, H, N, M, 64, float(scale)
     _lib.check(_lib.lib().mmdit_attn_bwd(C.byref(a), _s()), "mmdit_attn_bwd")
+    return dq_acc if dq is None else None
 
 
 # ------------------------------------------------------------- row kernels
@@ -288,9 +292,17 @@ def qknorm_rope_fwd(qkv, wq, wk, rope, d, tokens_per_sample):
     return out
 
 
-def qknorm_rope_bwd(dqk, qkv, wq, wk, rope, dqkv, dwq, dwk, d, tokens_per_sample):
+def qknorm_rope_bwd(dqk, qkv, wq, wk, rope, dqkv, dwq, dwk, d, tokens_per_sample, dq_acc=None, acc_off=0):
+    """dq_acc (fp32 [B, T, d] from attn_bwd(dq=None)): the q half of the gradient is read from it (this
+    stream's rows start at acc_off in every sample); only the k half of dqk is read then."""
     R = qkv.shape[0]
     cos, sin = rope if rope is not None else (None, None)
+    if dq_acc is not None:
+        _lib.check(_lib.lib().mmdit_qknorm_rope_bwd_acc(
+            _p(dq_acc), dq_acc.shape[1], acc_off, _p(dqk), _p(qkv), _p(wq), _p(wk), _p(cos), _p(sin), _p(dqkv),
+            _p(dwq), _p(dwk), R, d, dqk.stride(0), qkv.stride(0), dqkv.stride(0), tokens_per_sample, RMS_EPS,
+            _s()), "mmdit_qknorm_rope_bwd_acc")
+        return
     _lib.check(_lib.lib().mmdit_qknorm_rope_bwd(
         _p(dqk), _p(qkv), _p(wq), _p(wk), _p(cos), _p(sin), _p(dqkv), _p(dwq), _p(dwk), R, d,
         dqk.stride(0), qkv.stride(0), dqkv.stride(0), tokens_per_sample, RMS_EPS, _s()),

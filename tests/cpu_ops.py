@@ -45,8 +45,12 @@ def qknorm_rope_fwd(qkv, wq, wk, rope, d, tokens_per_sample):
     return _bf(torch.cat([q, k], 1))
 
 
-def qknorm_rope_bwd(dqk, qkv, wq, wk, rope, dqkv, dwq, dwk, d, tokens_per_sample):
+def qknorm_rope_bwd(dqk, qkv, wq, wk, rope, dqkv, dwq, dwk, d, tokens_per_sample, dq_acc=None, acc_off=0):
     H = d // 64
+    if dq_acc is not None:      # q half from the fp32 accumulator [B, T, d], rounded to bf16 like the old copy
+        Bn = qkv.shape[0] // tokens_per_sample
+        gq_in = _bf(dq_acc[:, acc_off:acc_off + tokens_per_sample].reshape(Bn * tokens_per_sample, d))
+        dqk = torch.cat([gq_in, dqk[:, d:]], 1)
     with torch.enable_grad():
         q = qkv[:, :d].float().detach().requires_grad_(True)
         k = qkv[:, d:2 * d].float().detach().requires_grad_(True)
@@ -135,11 +139,17 @@ def attn_bwd(q, k, v, o, lse, d_o, dq, dk, dv, B, H, N, M, scale):
         Q, K, V = (_joint(t[0], t[1], B, H, N, M).detach().requires_grad_(True) for t in (q, k, v))
         out = ((Q @ K.transpose(-1, -2)) * scale).softmax(-1) @ V
         g = torch.autograd.grad(out, (Q, K, V), _joint(d_o[0], d_o[1], B, H, N, M))
+    acc = None
     for grad, dst in zip(g, (dq, dk, dv)):
         gx, gc = _split(grad, B, H, N, M)
+        if dst is None:         # dq stays in the fp32 accumulator (joint layout, image rows first)
+            parts = [gx.float().view(B, N, H * 64)] + ([gc.float().view(B, M, H * 64)] if M else [])
+            acc = torch.cat(parts, 1).contiguous()
+            continue
         dst[0].copy_(gx)
         if M:
             dst[1].copy_(gc)
+    return acc
 
 
 # ------------------------------------------------------------------- row kernels

@@ -271,6 +271,20 @@ def group_elem():
         ok &= rel(dqkv[:, d:2 * d], kf.grad, "bwd dk", 1e-2)
         ok &= rel(dwq, wqr.grad, "bwd dwq", 5e-3)
         ok &= rel(dwk, wkr.grad, "bwd dwk", 5e-3)
+        # q half of the gradient read from an fp32 accumulator in the attention backward's joint layout
+        # [B, T, d] (this stream's rows at an offset inside every sample): must equal the bf16-copy path
+        pad = 7
+        acc = torch.randn(B, tokens + 2 * pad, d, device=dev)
+        acc[:, pad:pad + tokens] = dqk[:, :d].float().view(B, tokens, d)
+        dqkv2 = torch.zeros(R, 3 * d, device=dev, dtype=BF)
+        dwq2, dwk2 = torch.zeros(64, device=dev), torch.zeros(64, device=dev)
+        dqk_k_only = dqk.clone()
+        dqk_k_only[:, :d] = float("nan")       # the q half of dqk must not be read
+        ops.qknorm_rope_bwd(dqk_k_only, qkv, wq, wk, rope, dqkv2, dwq2, dwk2, d, tokens, dq_acc=acc, acc_off=pad)
+        same = bool(torch.equal(dqkv2[:, :2 * d], dqkv[:, :2 * d]))
+        print(f"    bwd from fp32 accumulator     identical to the bf16-copy path: {same}")
+        ok &= same
+        ok &= rel(dwq2, dwq, "bwd dwq (acc path)", 1e-5)
 
     print("[swiglu]")
     R, hid = 308, 1024

@@ -1,0 +1,11 @@
+#!/bin/bash
+mkdir -p gpurun_out/c16
+O=gpurun_out/c16
+run() { name=$1; shift; timeout 900 "$@" > $O/$name.log 2>&1; echo "exit=$?" >> $O/$name.log; tail -${TAILN:-3} $O/$name.log | cut -c1-200; }
+run pytest python -m pytest tests -x -q -m gpu
+MMDIT_ATTN_BWD_V2=0 run bench_v1 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-gpu-library-baseline
+run bench_v2 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-gpu-library-baseline
+MMDIT_ATTN_BWD_V2=0 run bench_v1b python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-gpu-library-baseline
+run bench_v2b python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-gpu-library-baseline
+run bench_cfg3 python bench.py --config cfg3 --batch 64 --steps 6 --warmup 3 --no-cpu-baseline --no-gpu-library-baseline
+run bench_cfg4 python bench.py --config cfg4 --steps 6 --warmup 3 --no-cpu-baseline --no-gpu-library-baseline

@@ -56,7 +56,14 @@ struct AttnFwdParams {
   float scale, scale_log2;
   const float* logit_bound;  // device scalar: upper bound of |scale * q.k| (QK-RMSNorm makes it small), or null
   int skip_if_bounded;       // the second-generation kernel (attn_fwd2.cu) serves launches whose bound is usable
+  int items;                 // > 0: 1-D grid whose CTAs loop over (sample, head, query tile) items -- the launch
+                             // behind attn_fwd2, which normally has nothing to do: a few hundred CTAs that exit at
+                             // once instead of B*H*tiles of them (ncu: 16 us of CTA launches for an empty grid)
 };
+
+__device__ __forceinline__ void mbar_inval(uint64_t* bar) {
+  asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 
 __global__ void __launch_bounds__(ATT_THREADS, 2)
 attn_fwd_kernel(const __grid_constant__ AttnFwdParams p) {
@@ -85,7 +92,14 @@ attn_fwd_kernel(const __grid_constant__ AttnFwdParams p) {
   const int ntx = (p.N + ATT_TILE - 1) / ATT_TILE;
   const int ntc = (p.M + ATT_TILE - 1) / ATT_TILE;
   const int nkv = ntx + ntc;
-  const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  // one item per CTA (3-D grid), or a loop over items (1-D grid, p.items > 0); every item sets up and
+  // tears down its barriers and its TMEM allocation exactly like a CTA of its own
+  for (int item = p.items > 0 ? (int)blockIdx.x : 0; item < (p.items > 0 ? p.items : 1); item += (int)gridDim.x) {
+  const bool first_item = p.items > 0 ? item == (int)blockIdx.x : true;
+  const bool last_item = p.items > 0 ? item + (int)gridDim.x >= p.items : true;
+  const int qt = p.items > 0 ? item % nkv : (int)blockIdx.x;
+  const int h = p.items > 0 ? (item / nkv) % p.H : (int)blockIdx.y;
+  const int b = p.items > 0 ? item / (nkv * p.H) : (int)blockIdx.z;
   const int qs = qt < ntx ? 0 : 1;                       // stream of the query tile
   const int q_row0 = (qs == 0 ? qt : qt - ntx) * ATT_TILE;
   const int q_rows = qs == 0 ? p.N : p.M;
@@ -121,8 +135,10 @@ attn_fwd_kernel(const __grid_constant__ AttnFwdParams p) {
       }
     }
     __syncwarp();
-    tmem_alloc(tmem_slot, 256);
-    tmem_relinquish();
+    if (first_item) {   // one TMEM allocation per CTA (the permit is relinquished: no second alloc possible)
+      tmem_alloc(tmem_slot, 256);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -369,7 +385,13 @@ attn_fwd_kernel(const __grid_constant__ AttnFwdParams p) {
   TL(tls++, 120);
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem_base, 256);
+  if (warp == 0 && last_item) tmem_dealloc(tmem_base, 256);
+  if (p.items > 0) {   // the next item re-initialises the barriers: invalidate them first
+    if (threadIdx.x == 0)
+      for (int i = 0; i < 9; ++i) mbar_inval(bars + i);
+    __syncthreads();
+  }
+  }   // item loop
 }
 
 // 4-D view of one operand of one stream: (64 | H | rows | B), head h at column h*64.
@@ -443,6 +465,10 @@ extern "C" int mmdit_attn_fwd(const mmdit_attn_args* a, void* stream) {
   }
   const int nt = (a->N + ATT_TILE - 1) / ATT_TILE + (a->M + ATT_TILE - 1) / ATT_TILE;
   dim3 grid(nt, a->H, a->B);
+  if (p.skip_if_bounded) {
+    p.items = nt * a->H * a->B;
+    grid = dim3(p.items < 2 * num_sms() ? p.items : 2 * num_sms());
+  }
   launch_k(attn_fwd_kernel, grid, dim3(ATT_THREADS), ATT_SMEM, static_cast<cudaStream_t>(stream), p);
   return check_launch("attn_fwd_kernel");
 }

@@ -45,10 +45,10 @@ def _unit_rms_heads(t, d, H):
     return t
 
 
-def attn_case(B, H, N, M, bwd=True, seed=0, bounded=False):
+def attn_case(B, H, N, M, bwd=True, seed=0, bounded=False, unusable_bound=False):
     torch.manual_seed(seed)
     d = H * 64
-    print(f"[attn] B={B} H={H} N={N} M={M} bounded={bounded}")
+    print(f"[attn] B={B} H={H} N={N} M={M} bounded={bounded} unusable_bound={unusable_bound}")
     qkv_x = torch.randn(B * N, 3 * d, device=dev).bfloat16()
     qkv_c = torch.randn(B * M, 3 * d, device=dev).bfloat16() if M else None
     bound = None
@@ -58,6 +58,8 @@ def attn_case(B, H, N, M, bwd=True, seed=0, bounded=False):
         one = torch.ones(64, device=dev)
         bound = ops.qk_logit_bound(one, one, one, one, 0.125)
         assert abs(float(bound) - 8.16) < 1e-4
+    if unusable_bound:   # a bound above 24: attn_fwd2 returns at once, the online-softmax kernel's item loop runs
+        bound = torch.full((1,), 30.0, device=dev)
     qs = (qkv_x[:, :d], qkv_c[:, :d] if M else None)
     ks = (qkv_x[:, d:2 * d], qkv_c[:, d:2 * d] if M else None)
     vs = (qkv_x[:, 2 * d:], qkv_c[:, 2 * d:] if M else None)
@@ -105,6 +107,8 @@ def group_attn():
     ok &= attn_case(2, 4, 256, 154, bounded=True)      # single-pass softmax against the QK-norm bound
     ok &= attn_case(2, 3, 240, 77, bounded=True)
     ok &= attn_case(2, 4, 1024, 154, bounded=True)     # 10 key tiles, 26-row last query tile (idle softmax warps)
+    ok &= attn_case(8, 12, 256, 154, bwd=False, unusable_bound=True)   # 384 items on 296 looping CTAs
+    ok &= attn_case(2, 3, 240, 77, bwd=False, unusable_bound=True)
     return ok
 
 

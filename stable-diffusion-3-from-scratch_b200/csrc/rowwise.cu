@@ -8,6 +8,8 @@
 // (dshift/dscale/dgate, per batch element) are accumulated in registers across
 // the rows a warp owns, folded once per block in shared memory and added to
 // the fp32 output with one atomic per column per block.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "mmdit_b200.h"
 
@@ -511,9 +513,21 @@ int mmdit_gate_residual_ln_fwd(const void* a, const void* gate, const void* resi
   return check_launch("gate_res_ln_fwd_kernel");
 }
 
+// Rows a block of the backward row kernels reduces before it writes one partial.  Measured
+// (tools/row_probe.py, LN-modulate bwd / gate bwd): 768 columns 28 / 25 us at 16 rows, 26 / 27 at 32,
+// 35 / 26 at 64; 1536 columns 66 / 46 us at 16, 59 / 41 at 32, 58 / 39 at 64.  MMDIT_ROW_RPB overrides.
+static int rows_per_block(int d) {
+  static const int forced = [] {
+    const char* e = getenv("MMDIT_ROW_RPB");
+    const int x = e ? atoi(e) : 0;
+    return x >= 4 && x <= 1024 ? x : 0;
+  }();
+  return forced ? forced : (d > 1024 ? 64 : 16);
+}
+
 int64_t mmdit_rowreduce_workspace_floats(int64_t rows, int32_t d, int64_t rows_per_batch) {
   if (rows <= 0 || d <= 0 || rows_per_batch <= 0) return 0;
-  const int64_t bpb = (rows_per_batch + 15) / 16;
+  const int64_t bpb = (rows_per_batch + rows_per_block(d) - 1) / rows_per_block(d);
   return (rows / rows_per_batch) * bpb * 2 * d;
 }
 
@@ -524,7 +538,7 @@ int mmdit_ln_modulate_bwd(const void* dy, const void* x, const float* mean, cons
   MMDIT_REQUIRE(dy && x && mean && rstd && scale && dx && dshift && dscale && workspace && rows > 0 &&
                     d % 8 == 0 && rows_per_batch > 0 && rows % rows_per_batch == 0,
                 MMDIT_ERR_ARG, "ln_modulate_bwd: bad arguments");
-  const int rpb = 16;
+  const int rpb = rows_per_block(d);
   const int bpb = (int)((rows_per_batch + rpb - 1) / rpb);
   const int nb = (int)(rows / rows_per_batch);
   const unsigned grid = (unsigned)(nb * bpb);
@@ -547,7 +561,7 @@ int mmdit_gate_bwd(const void* dout, const void* a, const void* gate, void* da, 
   MMDIT_REQUIRE(dout && a && gate && da && dgate && workspace && rows > 0 && d % 8 == 0 &&
                     rows_per_batch > 0 && rows % rows_per_batch == 0,
                 MMDIT_ERR_ARG, "gate_bwd: bad arguments");
-  const int rpb = 16;
+  const int rpb = rows_per_block(d);
   const int bpb = (int)((rows_per_batch + rpb - 1) / rpb);
   const int nb = (int)(rows / rows_per_batch);
   const unsigned grid = (unsigned)(nb * bpb);

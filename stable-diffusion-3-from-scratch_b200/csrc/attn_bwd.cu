@@ -894,34 +894,51 @@ attn_bwd2_kernel(const __grid_constant__ AttnBwdParams p, int items) {
   if (warp == 0) tmem_dealloc(tmem_base, 512);
 }
 
-// delta[b,h,t] = sum_e dO[b,t,h,e] * O[b,t,h,e]; 8 lanes per (row, head).
+// delta[b,h,t] = sum_e dO[b,t,h,e] * O[b,t,h,e]; 8 lanes per (row, head).  Both streams in one launch;
+// every thread also clears the 8 floats of the fp32 dQ accumulator that belong to its (row, head, part)
+// -- the accumulator is exactly 8 floats per thread of this grid, so the separate 80 MB memset node
+// (13 us per attention backward at the cfg2 shape) disappears.
+struct AttnDeltaParams {
+  const bf16* o[2];
+  const bf16* d_o[2];
+  long long ld_o[2], ld_do[2];
+  long long rows[2];          // B * rows_per_sample
+  int rows_per_sample[2];
+  float* delta;               // [B, H, T]
+  float* dq_acc;              // [B, T, H*64]
+  int H, T, N;
+};
 __global__ void __launch_bounds__(256)
-attn_delta_kernel(const bf16* __restrict__ o, const bf16* __restrict__ d_o, float* __restrict__ delta,
-                  long long rows, int H, long long ld_o, long long ld_do, int rows_per_sample,
-                  int t_off, int T) {
+attn_delta_kernel(const __grid_constant__ AttnDeltaParams p) {
   // (no early pdl_trigger: dependents are released when this grid exits)
   pdl_wait();   // programmatic dependent launch: the previous kernel's writes are visible from here
-  const long long total = rows * H * 8;
-  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long total0 = p.rows[0] * p.H * 8;
+  const long long total = total0 + p.rows[1] * p.H * 8;
+  long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   const bool active = idx < total;
+  const int s = (active && idx >= total0) ? 1 : 0;      // total0 is a multiple of 8: a head never straddles
+  if (s) idx -= total0;
   const long long rh = active ? idx / 8 : 0;
   const int part = (int)(idx & 7);
-  const long long row = rh / H;
-  const int h = (int)(rh % H);
+  const long long row = rh / p.H;
+  const int h = (int)(rh % p.H);
   float a[8], g[8];
   float acc = 0.f;
   if (active) {
-    load8(o + row * ld_o + h * 64 + part * 8, a);
-    load8(d_o + row * ld_do + h * 64 + part * 8, g);
+    load8(p.o[s] + row * p.ld_o[s] + h * 64 + part * 8, a);
+    load8(p.d_o[s] + row * p.ld_do[s] + h * 64 + part * 8, g);
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc += a[j] * g[j];
   }
 #pragma unroll
   for (int off = 1; off < 8; off <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-  if (active && part == 0) {
-    const long long bb = row / rows_per_sample;
-    const int t = t_off + (int)(row % rows_per_sample);
-    delta[(bb * H + h) * T + t] = acc;
+  if (active) {
+    const long long bb = row / p.rows_per_sample[s];
+    const int t = (s ? p.N : 0) + (int)(row % p.rows_per_sample[s]);
+    if (part == 0) p.delta[(bb * p.H + h) * p.T + t] = acc;
+    float* z = p.dq_acc + ((bb * p.T + t) * (long long)p.H + h) * 64 + part * 8;
+    *reinterpret_cast<float4*>(z) = make_float4(0.f, 0.f, 0.f, 0.f);
+    *reinterpret_cast<float4*>(z + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
   }
 }
 
@@ -969,11 +986,8 @@ extern "C" int mmdit_attn_bwd(const mmdit_attn_args* a, void* stream_) {
   const int rows[2] = {a->N, a->M};
   const int T = a->N + a->M;
   const int dmodel = a->H * 64;
-  cudaError_t e = cudaMemsetAsync(a->dq_acc, 0, sizeof(float) * (size_t)a->B * T * dmodel, stream);
-  if (e != cudaSuccess) {
-    set_last_error("attn_bwd: memset: %s", cudaGetErrorString(e));
-    return (int)e;
-  }
+  AttnDeltaParams dp;
+  memset(&dp, 0, sizeof(dp));
   for (int s = 0; s < 2; ++s) {
     if (rows[s] == 0) continue;
     MMDIT_REQUIRE(a->q[s] && a->k[s] && a->v[s] && a->o[s] && a->d_o[s] && a->dk[s] && a->dv[s],
@@ -1002,15 +1016,23 @@ extern "C" int mmdit_attn_bwd(const mmdit_attn_args* a, void* stream_) {
     p.dv[s] = static_cast<bf16*>(a->dv[s]);
     p.ld_dk[s] = a->ld_dk[s];
     p.ld_dv[s] = a->ld_dv[s];
-    // delta = rowsum(dO * O)
-    const long long nrows = (long long)a->B * rows[s];
-    const long long work = nrows * a->H * 8;
-    MMDIT_CARVEOUT(attn_delta_kernel);
-    launch_k(attn_delta_kernel, dim3((unsigned)((work + 255) / 256)), dim3(256), 0, stream, 
-        static_cast<const bf16*>(a->o[s]), static_cast<const bf16*>(a->d_o[s]), a->delta, nrows,
-        a->H, a->ld_o[s], a->ld_do[s], rows[s], s == 0 ? 0 : a->N, T);
+    dp.o[s] = static_cast<const bf16*>(a->o[s]);
+    dp.d_o[s] = static_cast<const bf16*>(a->d_o[s]);
+    dp.ld_o[s] = a->ld_o[s];
+    dp.ld_do[s] = a->ld_do[s];
+    dp.rows[s] = (long long)a->B * rows[s];
+    dp.rows_per_sample[s] = rows[s];
   }
-  int rc = check_launch("attn_delta_kernel", a->M > 0 ? 2 : 1);
+  // delta = rowsum(dO * O) of both streams, and the fp32 dQ accumulator cleared, in one launch
+  dp.delta = a->delta; dp.dq_acc = a->dq_acc;
+  dp.H = a->H; dp.T = T; dp.N = a->N;
+  if (dp.rows_per_sample[1] == 0) dp.rows_per_sample[1] = 1;
+  {
+    const long long work = (dp.rows[0] + dp.rows[1]) * a->H * 8;
+    MMDIT_CARVEOUT(attn_delta_kernel);
+    launch_k(attn_delta_kernel, dim3((unsigned)((work + 255) / 256)), dim3(256), 0, stream, dp);
+  }
+  int rc = check_launch("attn_delta_kernel");
   if (rc) return rc;
   p.lse = a->lse; p.delta = a->delta; p.dq_acc = a->dq_acc;
   p.B = a->B; p.H = a->H; p.N = a->N; p.M = a->M;

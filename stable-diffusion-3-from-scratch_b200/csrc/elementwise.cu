@@ -8,6 +8,8 @@
 //   rectified-flow noising, velocity loss, CFG+Euler update
 //                                                  (diff_model.py:229-241,419-429; model_trainer.py:429-446)
 //   column sums (bias gradients), row folds, dtype casts
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "mmdit_b200.h"
 
@@ -86,7 +88,7 @@ qknorm_rope_fwd_kernel(const bf16* __restrict__ qkv, const float* __restrict__ w
 // instead of a bf16 copy: the separate convert pass (write + re-read of a [R, d] bf16 tensor and one
 // launch per stream) disappears; the value is rounded to bf16 first, exactly as the copy was.
 template <bool DQ_F32>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 qknorm_rope_bwd_kernel(const float* __restrict__ dq_acc, int acc_tokens, int acc_tok_off,
                        const bf16* __restrict__ dqk, const bf16* __restrict__ qkv,
                        const float* __restrict__ wq, const float* __restrict__ wk,
@@ -545,7 +547,12 @@ __global__ void qk_logit_bound_kernel(const float* __restrict__ wq_x, const floa
 
 static inline unsigned grid_for(long long work_items, int threads) {
   long long blocks = (work_items + threads - 1) / threads;
-  const long long cap = (long long)num_sms() * 16;
+  static const int per_sm = [] {   // blocks per SM of the grid-stride kernels (tuning knob)
+    const char* e = getenv("MMDIT_GRID_CAP");
+    const int x = e ? atoi(e) : 16;
+    return x >= 1 && x <= 64 ? x : 16;
+  }();
+  const long long cap = (long long)num_sms() * per_sm;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   return (unsigned)blocks;
@@ -571,6 +578,15 @@ int mmdit_qknorm_rope_fwd(const void* qkv, const float* wq, const float* wk, con
   return check_launch("qknorm_rope_fwd_kernel");
 }
 
+static unsigned qkn_cap() {   // resident blocks per SM x waves of the QK-norm backward grid (tuning knob)
+  static const unsigned v = [] {
+    const char* e = getenv("MMDIT_QKN_CAP");
+    const int x = e ? atoi(e) : 3;
+    return (unsigned)(x >= 1 && x <= 64 ? x : 3);
+  }();
+  return v;
+}
+
 int mmdit_qknorm_rope_bwd(const void* dqk, const void* qkv, const float* wq, const float* wk,
                           const float* rope_cos, const float* rope_sin, void* dqkv, float* dwq,
                           float* dwk, int64_t rows, int32_t d, int64_t ld_g, int64_t ld_in,
@@ -580,7 +596,7 @@ int mmdit_qknorm_rope_bwd(const void* dqk, const void* qkv, const float* wq, con
                 MMDIT_ERR_ARG, "qknorm_rope_bwd: bad arguments");
   const long long work = rows * (long long)(d / 8);
   unsigned grid = grid_for(work, 256);
-  const unsigned cap = (unsigned)num_sms() * 4;  // fewer, longer-lived blocks: fewer atomics
+  const unsigned cap = (unsigned)num_sms() * qkn_cap();  // fewer, longer-lived blocks: fewer atomics
   if (grid > cap) grid = cap;
   MMDIT_CARVEOUT(qknorm_rope_bwd_kernel<false>);
   launch_k(qknorm_rope_bwd_kernel<false>, grid, dim3(256), 0, (cudaStream_t)stream, (const float*)nullptr, 0, 0,
@@ -601,7 +617,7 @@ int mmdit_qknorm_rope_bwd_acc(const float* dq_acc, int32_t acc_tokens, int32_t a
                 MMDIT_ERR_ARG, "qknorm_rope_bwd_acc: bad arguments");
   const long long work = rows * (long long)(d / 8);
   unsigned grid = grid_for(work, 256);
-  const unsigned cap = (unsigned)num_sms() * 4;  // fewer, longer-lived blocks: fewer atomics
+  const unsigned cap = (unsigned)num_sms() * qkn_cap();  // fewer, longer-lived blocks: fewer atomics
   if (grid > cap) grid = cap;
   MMDIT_CARVEOUT(qknorm_rope_bwd_kernel<true>);
   launch_k(qknorm_rope_bwd_kernel<true>, grid, dim3(256), 0, (cudaStream_t)stream, dq_acc, (int)acc_tokens,

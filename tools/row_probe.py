@@ -87,7 +87,7 @@ def timeit(fn, nbuf, iters=5):
 def perf(name, Bn, T, d):
     R = Bn * T
     per = R * d * 2   # bytes of one bf16 [R, d] tensor
-    nbuf = max(2, int(400e6 // (5 * per)) + 1)   # > 126 MB of L2 between two uses of the same set
+    nbuf = max(2, int(400e6 // (5 * per)) + 1)   # > 126 MB of L2 between two uses of the same set (row kernels)
     sets = [make(Bn, T, d, seed=i) for i in range(nbuf)]
     for s in sets:
         s["xo"], s["y"], s["mean"], s["rstd"] = ops.gate_residual_ln_fwd(s["a"], s["gate"], s["resid"], s["shift"], s["scale"], T)
@@ -108,6 +108,30 @@ def perf(name, Bn, T, d):
     add("ln_modulate_bwd (dres)", 4 * per, lambda i: ops.ln_modulate_bwd(
         S(i)["dy"], S(i)["xo"], S(i)["mean"], S(i)["rstd"], S(i)["scale"], S(i)["dres"], S(i)["dmod"][0], S(i)["dmod"][1], T))
     add("gate_bwd", 3 * per, lambda i: ops.gate_bwd(S(i)["dy"], S(i)["a"], S(i)["gate"], S(i)["dgate"], S(i)["dab"], T))
+    # QK-RMSNorm + RoPE and SwiGLU backward at the same row count (image stream: RoPE on)
+    H = d // 64
+    side = int(round(T ** 0.5))
+    rope = None
+    if side * side == T:
+        ang = torch.rand(T, 32, device=dev)
+        rope = (torch.cos(ang).contiguous(), torch.sin(ang).contiguous())
+    wq, wk = torch.rand(64, device=dev) + 0.5, torch.rand(64, device=dev) + 0.5
+    for s in sets:
+        g = torch.Generator(device=dev).manual_seed(7)
+        s["qkv"] = torch.randn(R, 3 * d, device=dev, generator=g).bfloat16()
+        s["dqk"] = torch.randn(R, 2 * d, device=dev, generator=g).bfloat16()
+        s["dqkv"] = torch.empty(R, 3 * d, device=dev, dtype=BF)
+        s["dq_acc"] = torch.randn(Bn, T, d, device=dev, generator=g)
+        s["dw"] = torch.zeros(2, 64, device=dev)
+        s["h12"] = torch.randn(R, 8 * d, device=dev, generator=g).bfloat16()
+        s["dact"] = torch.randn(R, 4 * d, device=dev, generator=g).bfloat16()
+        s["db"] = torch.zeros(8 * d, device=dev)
+    add("qknorm_rope_fwd", 4 * per, lambda i: ops.qknorm_rope_fwd(S(i)["qkv"], wq, wk, rope, d, T))
+    add("qknorm_rope_bwd (bf16 dq)", 6 * per, lambda i: ops.qknorm_rope_bwd(
+        S(i)["dqk"], S(i)["qkv"], wq, wk, rope, S(i)["dqkv"], S(i)["dw"][0], S(i)["dw"][1], d, T))
+    add("qknorm_rope_bwd (fp32 dq_acc)", 7 * per, lambda i: ops.qknorm_rope_bwd(
+        S(i)["dqk"], S(i)["qkv"], wq, wk, rope, S(i)["dqkv"], S(i)["dw"][0], S(i)["dw"][1], d, T, dq_acc=S(i)["dq_acc"]))
+    add("swiglu_bwd", 20 * per, lambda i: ops.swiglu_bwd(S(i)["dact"], S(i)["h12"], S(i)["db"]))
     print(f"[perf {name}] B={Bn} rows/sample={T} d={d}  ({nbuf} rotating buffer sets, {per / 1e6:.1f} MB per tensor)")
     for tag, us, gbs in rows:
         print(f"    {tag:30s} {us:8.1f} us  {gbs:7.0f} GB/s  {gbs / HBM_PEAK:5.2f} of HBM peak")

@@ -300,7 +300,7 @@ ln_mod_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
 // forward was o = a*g[b] + x.  da = do*g[b]; dg[b] += sum_rows do*a;
 // dab[b] += sum_rows da (per-batch partial of the bias gradient, optional).
 template <int NC>
-__global__ void __launch_bounds__(BWD_THREADS)
+__global__ void __launch_bounds__(BWD_THREADS, NC <= 3 ? 4 : 2)
 gate_bwd_kernel(const bf16* __restrict__ dout, const bf16* __restrict__ a,
                 const bf16* __restrict__ gate, bf16* __restrict__ da, float* __restrict__ partial,
                 int d, long long rows_per_batch, long long ld_gate, int rows_per_block,
@@ -513,21 +513,33 @@ int mmdit_gate_residual_ln_fwd(const void* a, const void* gate, const void* resi
   return check_launch("gate_res_ln_fwd_kernel");
 }
 
-// Rows a block of the backward row kernels reduces before it writes one partial.  Measured
-// (tools/row_probe.py, LN-modulate bwd / gate bwd): 768 columns 28 / 25 us at 16 rows, 26 / 27 at 32,
-// 35 / 26 at 64; 1536 columns 66 / 46 us at 16, 59 / 41 at 32, 58 / 39 at 64.  MMDIT_ROW_RPB overrides.
-static int rows_per_block(int d) {
+// Rows a block of the backward row kernels reduces before it writes one partial: chosen so that the
+// grid is ONE wave of resident blocks (blocks per SM from the occupancy calculator x SMs, split evenly
+// over the samples).  With the fixed 16 rows of round 1 the cfg2 grids were 1.73 (image) and 1.08 (text)
+// waves.  MMDIT_ROW_RPB overrides.  Never below 8 rows (bounds the partial workspace).
+constexpr int ROW_RPB_MIN = 8;
+static int rows_per_block(const void* kernel, size_t smem, long long rows_per_batch, int nb) {
   static const int forced = [] {
     const char* e = getenv("MMDIT_ROW_RPB");
     const int x = e ? atoi(e) : 0;
-    return x >= 4 && x <= 1024 ? x : 0;
+    return x >= ROW_RPB_MIN && x <= 1024 ? x : 0;
   }();
-  return forced ? forced : (d > 1024 ? 64 : 16);
+  if (forced) return forced;
+  int occ = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, BWD_THREADS, smem) != cudaSuccess || occ < 1) {
+    cudaGetLastError();
+    occ = 2;
+  }
+  long long per_sample = (long long)occ * num_sms() / nb;
+  if (per_sample < 1) per_sample = 1;
+  long long rpb = (rows_per_batch + per_sample - 1) / per_sample;
+  if (rpb < ROW_RPB_MIN) rpb = ROW_RPB_MIN;
+  return (int)rpb;
 }
 
 int64_t mmdit_rowreduce_workspace_floats(int64_t rows, int32_t d, int64_t rows_per_batch) {
   if (rows <= 0 || d <= 0 || rows_per_batch <= 0) return 0;
-  const int64_t bpb = (rows_per_batch + rows_per_block(d) - 1) / rows_per_block(d);
+  const int64_t bpb = (rows_per_batch + ROW_RPB_MIN - 1) / ROW_RPB_MIN;   // upper bound over every block size
   return (rows / rows_per_batch) * bpb * 2 * d;
 }
 
@@ -538,12 +550,13 @@ int mmdit_ln_modulate_bwd(const void* dy, const void* x, const float* mean, cons
   MMDIT_REQUIRE(dy && x && mean && rstd && scale && dx && dshift && dscale && workspace && rows > 0 &&
                     d % 8 == 0 && rows_per_batch > 0 && rows % rows_per_batch == 0,
                 MMDIT_ERR_ARG, "ln_modulate_bwd: bad arguments");
-  const int rpb = rows_per_block(d);
-  const int bpb = (int)((rows_per_batch + rpb - 1) / rpb);
   const int nb = (int)(rows / rows_per_batch);
-  const unsigned grid = (unsigned)(nb * bpb);
   const size_t smem = (size_t)BWD_WARPS * 2 * d * sizeof(float);
   MMDIT_REQUIRE(smem <= 48 * 1024, MMDIT_ERR_UNSUPPORTED, "ln_modulate_bwd: d=%d too wide", d);
+  int rpb = 16;
+  DISPATCH_NC(d, rpb = rows_per_block((const void*)ln_mod_bwd_kernel<NC>, smem, rows_per_batch, nb));
+  const int bpb = (int)((rows_per_batch + rpb - 1) / rpb);
+  const unsigned grid = (unsigned)(nb * bpb);
   DISPATCH_NC(d, MMDIT_CARVEOUT(ln_mod_bwd_kernel<NC>); (launch_k(ln_mod_bwd_kernel<NC>, grid, dim3(BWD_THREADS), smem, (cudaStream_t)stream, 
                      (const bf16*)dy, (const bf16*)x, mean, rstd, (const bf16*)scale,
                      (const bf16*)dres, (bf16*)dx, workspace, d, rows_per_batch, ld_mod, rpb, bpb)));
@@ -561,12 +574,13 @@ int mmdit_gate_bwd(const void* dout, const void* a, const void* gate, void* da, 
   MMDIT_REQUIRE(dout && a && gate && da && dgate && workspace && rows > 0 && d % 8 == 0 &&
                     rows_per_batch > 0 && rows % rows_per_batch == 0,
                 MMDIT_ERR_ARG, "gate_bwd: bad arguments");
-  const int rpb = rows_per_block(d);
-  const int bpb = (int)((rows_per_batch + rpb - 1) / rpb);
   const int nb = (int)(rows / rows_per_batch);
-  const unsigned grid = (unsigned)(nb * bpb);
   const size_t smem = (size_t)BWD_WARPS * 2 * d * sizeof(float);
   MMDIT_REQUIRE(smem <= 48 * 1024, MMDIT_ERR_UNSUPPORTED, "gate_bwd: d=%d too wide", d);
+  int rpb = 16;
+  DISPATCH_NC(d, rpb = rows_per_block((const void*)gate_bwd_kernel<NC>, smem, rows_per_batch, nb));
+  const int bpb = (int)((rows_per_batch + rpb - 1) / rpb);
+  const unsigned grid = (unsigned)(nb * bpb);
   DISPATCH_NC(d, MMDIT_CARVEOUT(gate_bwd_kernel<NC>); (launch_k(gate_bwd_kernel<NC>, grid, dim3(BWD_THREADS), smem, (cudaStream_t)stream, 
                      (const bf16*)dout, (const bf16*)a, (const bf16*)gate, (bf16*)da, workspace, d,
                      rows_per_batch, ld_gate, rpb, bpb)));

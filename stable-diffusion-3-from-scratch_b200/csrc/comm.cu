@@ -211,12 +211,14 @@ extern "C" int mmdit_allreduce_mean_f32(const mmdit_comm* c, int64_t offset, int
   p.scale = 1.0f / (float)c->world;
   if (ctas <= 0) ctas = 48;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  static int mult = -1;
-  if (mult < 0) {
+  // peer loads in flight per thread, as a multiple of the per-world base.  Measured at 8 GPUs (cfg2 step,
+  // profiles/r02_bench_cfg2_n8_*): x1 31.5 ms, x2 30.6 ms, x4 31.6 ms -> x2 at world 8; MMDIT_COMM_UNROLL overrides.
+  static const int forced = [] {
     const char* e = getenv("MMDIT_COMM_UNROLL");
-    mult = e ? atoi(e) : 1;
-    if (mult != 2 && mult != 4) mult = 1;
-  }
+    const int m = e ? atoi(e) : 0;
+    return (m == 1 || m == 2 || m == 4) ? m : 0;
+  }();
+  const int mult = forced ? forced : (c->world == 8 ? 2 : 1);
 #define COMM_LAUNCH(WW, UU)                                            \
   do {                                                                 \
     MMDIT_CARVEOUT((allreduce_mean_kernel<WW, UU>));                   \

@@ -56,9 +56,14 @@ enum {
   MMDIT_EPI_RESID = 3,     /* D = acc + bias + resid                            */
   MMDIT_EPI_SWIGLU = 4,    /* B = [gate rows; up rows] (xformers w12, MLP.py:19): D[M,N/2] = silu(g)*u,
                               aux[M,N] = acc+bias (bf16, required); needs N % 256 == 0, M > 128 */
-  MMDIT_EPI_QKNORM = 5     /* B = [q; k; v] rows (N = 3d): D[M,N] = acc (+bias), aux[M,2d] = per-head
+  MMDIT_EPI_QKNORM = 5,    /* B = [q; k; v] rows (N = 3d): D[M,N] = acc (+bias), aux[M,2d] = per-head
                               RMSNorm * weight (+ 2-D RoPE) of the q and k columns (Attention.py:61-64,
-                              130-134,174-194); experimental, not yet validated on hardware */
+                              130-134,174-194); validated, measured slower than the separate kernel */
+  MMDIT_EPI_SWIGLU_BWD = 6 /* data gradient of xformers' w3 fused with the SwiGLU backward (MLP.py:19,32):
+                              g = bf16(acc) [M,N = hidden]; aux[M,2N] = [x1 | x2] (INPUT, the saved
+                              pre-activations); D[M,2N] = [g x2 silu'(x1) | g silu(x1)];
+                              colsum_partial (optional) = column sums of every 32-row strip of D.
+                              Needs N % 256 == 0, M % 128 == 0, M > 128, no bias */
 };
 
 typedef struct mmdit_gemm_args {
@@ -94,6 +99,8 @@ typedef struct mmdit_gemm_args {
   const void* rope_sin;
   int32_t qk_tokens;     /* tokens per sample: position of row m is m % qk_tokens */
   float qk_eps;
+  /* MMDIT_EPI_SWIGLU_BWD only */
+  float* colsum_partial; /* fp32 [M/32, 2N] or NULL */
 } mmdit_gemm_args;
 
 int mmdit_gemm_bf16(const mmdit_gemm_args* args, void* stream);

@@ -29,6 +29,7 @@ constexpr int GEMM_THREADS = 256;
 constexpr int SMEM_BUDGET = 227 * 1024;
 constexpr int BAR_BYTES = 256;
 constexpr int EPI_STAGE_BYTES = 4 * 32 * 64 * 4;  // 4 warps x (32 rows x 64 fp32)
+constexpr int EPI_STAGE_BYTES_SWIGLU_BWD = 4 * 6 * 4096;  // 4 warps x (2 x (x1, x2) in; d1, d2 out) 32 x 64 bf16 tiles
 
 struct GemmParams {
   CUtensorMap tmA, tmB;
@@ -62,6 +63,8 @@ struct GemmParams {
   int qk_d;                // model width: columns [0,d) = q, [d,2d) = k, [2d,3d) = v
   int qk_tokens;           // tokens per sample (row -> position for RoPE)
   float qk_eps;
+  // EV_SWIGLU_BWD
+  float* colsum_partial;   // [M/32, 2N] fp32 column sums of every 32-row strip of D, or null
 };
 
 __device__ __forceinline__ float bias_at(const GemmParams& p, int n) {
@@ -147,7 +150,21 @@ __device__ __forceinline__ void epilogue8(const GemmParams& p, long long m, long
 // (all run-time flags resolved at compile time, full 8-column vectors, 16-byte aligned rows);
 // EV_GENERIC keeps every option behind run-time flags (tails, remap, SiLU, odd alignments).
 enum { EV_GENERIC = 0, EV_BF16 = 1, EV_BF16_BIAS = 2, EV_GATE = 3, EV_F32 = 4, EV_F32_ATOMIC = 5,
-       EV_BF16_TMA = 6, EV_SWIGLU_TMA = 7, EV_QKNORM_TMA = 8 };
+       EV_BF16_TMA = 6, EV_SWIGLU_TMA = 7, EV_QKNORM_TMA = 8, EV_SWIGLU_BWD = 9 };
+// EV_SWIGLU_BWD (CTA pairs only): the GEMM is the data gradient of xformers' w3 (MLP.py:19,32),
+// acc = dY W3 = d(silu(x1) * x2) [M, N = hidden]; the epilogue applies the SwiGLU backward to it against
+// the saved pre-activations aux = [x1 | x2] ([M, 2N]) and writes D = [d x1 | d x2] ([M, 2N]) -- the
+// activation-gradient tensor is never written or re-read and the separate swiglu_bwd pass (10 B per
+// hidden element at 0.7-0.8 of the HBM rate, 2.0 ms of the cfg2 step) disappears.  Per epilogue warp and
+// 64-column chunk: the x1 / x2 tiles of its 32 rows arrive by TMA (issued one chunk ahead by the warp
+// itself), each thread reads its row from the swizzled tiles, computes d1 / d2 from the bf16-rounded
+// accumulator exactly as swiglu_bwd_kernel does, and the two output tiles leave by TMA stores; the
+// column sums of the strip (w12 bias gradient) are read back from the output tiles, two columns per lane.
+// Validated bit-identical to gemm + swiglu_bwd (tools/gemm_probe.py swiglu_bwd); alone it saves 12-66 us per
+// GEMM, inside the cfg2 step nothing (the 4 epilogue warps need ~2.4x the mainloop time per tile), so
+// the trainer keeps the two kernels unless MMDIT_FUSED_SWIGLU_BWD=1.  Two hazards found on hardware are
+// written down at the places they bit: the x tiles must be double-buffered, and the output tiles need a
+// bar.sync (not __syncwarp) between the st.shared and the TMA store.
 // EV_QKNORM_TMA (experimental, MMDIT_FUSED_QKNORM=1; NOT yet validated on hardware): the packed
 // q|k|v projection writes the raw projection (D, needed by the backward) and, for the q and k
 // columns, the per-head RMSNorm * weight followed by the 2-D RoPE rotation (aux = [M, 2d]) --
@@ -280,11 +297,13 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
 
   // epilogue staging: per epilogue warp 32 rows x 64 fp32 (16-byte chunks XOR-swizzled by row)
   uint8_t* stage_buf = smem + stages * stage_bytes;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(stage_buf + EPI_STAGE_BYTES);
+  constexpr int kEpiBytes = EV == EV_SWIGLU_BWD ? EPI_STAGE_BYTES_SWIGLU_BWD : EPI_STAGE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(stage_buf + kEpiBytes);
   uint64_t* empty_bar = full_bar + MAX_STAGES;
   uint64_t* tmem_full = empty_bar + MAX_STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  [[maybe_unused]] uint64_t* epi_in = tmem_empty + 3;   // [4 warps][2 buffers] EV_SWIGLU_BWD: x1 / x2 tiles landed
 
   const uint32_t tmem_cols = 2u * block_n;  // 128 / 256 / 512: powers of two
 
@@ -301,6 +320,8 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
       mbar_init(&tmem_full[s], 1);
       mbar_init(&tmem_empty[s], PAIR ? 8 : 4);  // one arrive per epilogue warp (of both CTAs)
     }
+    if constexpr (EV == EV_SWIGLU_BWD)
+      for (int w = 0; w < 8; ++w) mbar_init(&epi_in[w], 1);
     mbar_fence_init();
   }
   if (warp == 2) {
@@ -419,6 +440,19 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
     uint32_t aphase = 0;
     const uint32_t leader_tmem_empty = PAIR ? mapa_u32(smem_u32(&tmem_empty[0]), 0) : 0u;
     [[maybe_unused]] int tma_buf = 0;
+    [[maybe_unused]] uint32_t epi_q = 0;   // EV_SWIGLU_BWD: chunks processed so far (x-tile buffer = q & 1)
+    if constexpr (EV == EV_SWIGLU_BWD) {
+      if (unit0 < total_work && elect_one()) {   // x1 / x2 tiles of this warp's first chunk
+        const int tile0 = unit0 / p.split_k;
+        const long long mf = static_cast<long long>(PAIR ? (tile0 % p.tiles_m) * 2 + (int)rank : tile0 % p.tiles_m) * BLOCK_M + ew * 32;
+        const int nf = (tile0 / p.tiles_m) * 256;
+        uint8_t* wb = stage_buf + ew * 24576;
+        mbar_expect_tx(&epi_in[2 * ew], 2 * 4096);
+        tma_load_2d(wb, &p.tmAux, &epi_in[2 * ew], nf, static_cast<int>(mf));
+        tma_load_2d(wb + 4096, &p.tmAux, &epi_in[2 * ew], p.N + nf, static_cast<int>(mf));
+      }
+      __syncwarp();
+    }
     for (int work = unit0; work < total_work; work += nunits) {
       const int tile = work / p.split_k;
       const int m_blk = PAIR ? (tile % p.tiles_m) * 2 + (int)rank : tile % p.tiles_m;
@@ -591,6 +625,106 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
           }
           stage_tile(gq, &p.tmD, n);
         }
+      } else if constexpr (EV == EV_SWIGLU_BWD) {
+        uint8_t* wbase = stage_buf + ew * 24576;   // [buf 0: x1, x2][buf 1: x1, x2][d1][d2], 4 KiB each
+        uint8_t* tD1 = wbase + 16384, *tD2 = wbase + 20480;
+        const int hid = p.N;
+        for (int c = 0; c < 4; ++c, ++epi_q) {
+          const int n = n_blk * 256 + c * 64;
+          const int buf = epi_q & 1;
+          uint8_t* tX1 = wbase + buf * 8192, *tX2 = tX1 + 4096;
+          {
+            // x1 / x2 tiles of the NEXT chunk (of this tile or of the next work unit) into the other buffer:
+            // its previous contents were consumed by the arithmetic of the chunk before this one.  (A
+            // single-buffered refill issued right after this chunk's ld.shared corrupted ~1e-6 of the
+            // elements even with the loads consumed first; issued after the chunk's stores it was clean.)
+            int n_next = n + 64;
+            long long m_next = m0;
+            bool has_next = true;
+            if (c == 3) {
+              const int work2 = work + nunits;
+              has_next = work2 < total_work;
+              const int tile2 = work2 / p.split_k;
+              m_next = static_cast<long long>(PAIR ? (tile2 % p.tiles_m) * 2 + (int)rank : tile2 % p.tiles_m) * BLOCK_M + ew * 32;
+              n_next = (tile2 / p.tiles_m) * 256;
+            }
+            if (has_next && elect_one()) {
+              uint64_t* nb = &epi_in[2 * ew + (buf ^ 1)];
+              uint8_t* nx = wbase + (buf ^ 1) * 8192;
+              mbar_expect_tx(nb, 2 * 4096);
+              tma_load_2d(nx, &p.tmAux, nb, n_next, static_cast<int>(m_next));
+              tma_load_2d(nx + 4096, &p.tmAux, nb, hid + n_next, static_cast<int>(m_next));
+            }
+            __syncwarp();
+          }
+          uint32_t r0[32], r1[32];
+          tmem_ld32(taddr + c * 64, r0);
+          tmem_ld32(taddr + c * 64 + 32, r1);
+          tmem_ld_wait();
+          if (c == 3) {  // accumulator drained: hand the TMEM stage back
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              if constexpr (PAIR) mbar_arrive_cluster(leader_tmem_empty + as * 8);
+              else mbar_arrive(&tmem_empty[as]);
+            }
+          }
+          // this thread's row of the x1 / x2 tiles (128B-swizzled, as TMA wrote them)
+          mbar_wait(&epi_in[2 * ew + buf], (epi_q >> 1) & 1u);
+          uint32_t x1p[32], x2p[32];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint4 u = *reinterpret_cast<const uint4*>(tX1 + lane * 128 + ((j ^ (lane & 7)) << 4));
+            const uint4 v = *reinterpret_cast<const uint4*>(tX2 + lane * 128 + ((j ^ (lane & 7)) << 4));
+            x1p[4 * j] = u.x; x1p[4 * j + 1] = u.y; x1p[4 * j + 2] = u.z; x1p[4 * j + 3] = u.w;
+            x2p[4 * j] = v.x; x2p[4 * j + 1] = v.y; x2p[4 * j + 2] = v.z; x2p[4 * j + 3] = v.w;
+          }
+          // d1 = g x2 sg (1 + x1 (1 - sg)),  d2 = g x1 sg   with g rounded to bf16 (as the unfused path stores it)
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const uint32_t* src = j < 16 ? &r0[2 * j] : &r1[2 * (j - 16)];
+            const float g0 = __bfloat162float(__float2bfloat16(__uint_as_float(src[0])));
+            const float g1 = __bfloat162float(__float2bfloat16(__uint_as_float(src[1])));
+            const float2 a = unpack_bf16x2(x1p[j]), b = unpack_bf16x2(x2p[j]);
+            const float s0 = __fdividef(1.f, 1.f + __expf(-a.x)), s1 = __fdividef(1.f, 1.f + __expf(-a.y));
+            x1p[j] = pack_bf16x2(g0 * b.x * s0 * (1.f + a.x * (1.f - s0)), g1 * b.y * s1 * (1.f + a.y * (1.f - s1)));
+            x2p[j] = pack_bf16x2(g0 * (a.x * s0), g1 * (a.y * s1));
+          }
+          if (elect_one()) tma_wait_group_read0();   // the previous chunk's stores have read the output tiles
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            *reinterpret_cast<uint4*>(tD1 + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+                make_uint4(x1p[4 * j], x1p[4 * j + 1], x1p[4 * j + 2], x1p[4 * j + 3]);
+            *reinterpret_cast<uint4*>(tD2 + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+                make_uint4(x2p[4 * j], x2p[4 * j + 1], x2p[4 * j + 2], x2p[4 * j + 3]);
+          }
+          fence_proxy_async_smem();
+          // bar.sync (not bar.warp.sync): it also drains this warp's pending st.shared.  With __syncwarp the
+          // store below occasionally read a tile whose LAST 16-byte chunk of a few rows was still the
+          // previous chunk's (single-buffered tiles leave no slack; seen as ~1e-6 of the elements).
+          named_bar_sync(8 + ew, 32);
+          if (!(p.debug & 1) && elect_one()) {
+            tma_store_2d(&p.tmD, tD1, n, static_cast<int>(m0));
+            tma_store_2d(&p.tmD, tD2, hid + n, static_cast<int>(m0));
+            tma_commit_group();
+          }
+          __syncwarp();   // reconverge before the next chunk's warp-collective tcgen05.ld
+          if (p.colsum_partial) {   // column sums of this 32-row strip: lane l owns columns 2l, 2l+1 of the chunk
+            float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+            const int wofs = (lane & 3) * 4, jch = lane >> 2;
+#pragma unroll 8
+            for (int r = 0; r < 32; ++r) {
+              const int off = r * 128 + ((jch ^ (r & 7)) << 4) + wofs;
+              const float2 u = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(tD1 + off));
+              const float2 v = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(tD2 + off));
+              a0 += u.x; a1 += u.y; b0 += v.x; b1 += v.y;
+            }
+            float* dst = p.colsum_partial + (m0 >> 5) * (2LL * hid) + n + 2 * lane;
+            *reinterpret_cast<float2*>(dst) = make_float2(a0, a1);
+            *reinterpret_cast<float2*>(dst + hid) = make_float2(b0, b1);
+          }
+        }
       } else if constexpr (EV == EV_BF16_TMA) {
         uint8_t* sbase = stage_buf + ew * (32 * 64 * 4);   // two 4 KiB bf16 tiles (1024 B aligned)
         for (int c = 0; c < nchunks; ++c) {
@@ -699,7 +833,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
       as ^= 1;
       if (as == 0) aphase ^= 1;
     }
-    if constexpr (EV == EV_BF16_TMA || EV == EV_SWIGLU_TMA || EV == EV_QKNORM_TMA) {
+    if constexpr (EV == EV_BF16_TMA || EV == EV_SWIGLU_TMA || EV == EV_QKNORM_TMA || EV == EV_SWIGLU_BWD) {
       if (elect_one()) tma_wait_group0();  // staging tiles must outlive their stores
     }
   }
@@ -787,7 +921,8 @@ extern "C" int mmdit_gemm_bf16(const mmdit_gemm_args* a, void* stream_) {
   MMDIT_REQUIRE(!(a->accumulate && !a->d_fp32), MMDIT_ERR_ARG, "gemm: accumulate needs fp32 D");
   MMDIT_REQUIRE(a->epilogue == MMDIT_EPI_NONE || a->epilogue == MMDIT_EPI_GATE_RESID ||
                     a->epilogue == MMDIT_EPI_SILU || a->epilogue == MMDIT_EPI_RESID ||
-                    a->epilogue == MMDIT_EPI_SWIGLU || a->epilogue == MMDIT_EPI_QKNORM,
+                    a->epilogue == MMDIT_EPI_SWIGLU || a->epilogue == MMDIT_EPI_QKNORM ||
+                    a->epilogue == MMDIT_EPI_SWIGLU_BWD,
                 MMDIT_ERR_UNSUPPORTED, "gemm: epilogue %d not supported", a->epilogue);
   if (a->epilogue == MMDIT_EPI_GATE_RESID)
     MMDIT_REQUIRE(a->gate && a->rows_per_gate > 0 && a->resid, MMDIT_ERR_ARG,
@@ -804,6 +939,16 @@ extern "C" int mmdit_gemm_bf16(const mmdit_gemm_args* a, void* stream_) {
                   MMDIT_ERR_UNSUPPORTED,
                   "gemm: the SwiGLU epilogue needs aux, bf16 D [M,N/2], K-major B, N %% 256 == 0, M > 128, "
                   "16-byte aligned rows and an fp32 bias");
+  }
+  const bool swiglu_bwd = a->epilogue == MMDIT_EPI_SWIGLU_BWD;
+  if (swiglu_bwd) {
+    auto al = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+    MMDIT_REQUIRE(a->aux && !a->d_fp32 && !a->accumulate && a->split_k <= 1 && a->remap_rows == 0 && !a->bias &&
+                      a->N % 256 == 0 && a->M % BLOCK_M == 0 && a->M > BLOCK_M && al(a->D) && al(a->aux) &&
+                      a->ldd % 8 == 0 && a->ld_aux % 8 == 0 && (!a->colsum_partial || al(a->colsum_partial)),
+                  MMDIT_ERR_UNSUPPORTED,
+                  "gemm: the SwiGLU-backward epilogue needs aux [M,2N], bf16 D [M,2N], no bias, N %% 256 == 0, "
+                  "M %% 128 == 0, M > 128 and 16-byte aligned rows");
   }
   const bool qknorm = a->epilogue == MMDIT_EPI_QKNORM;
   if (qknorm) {
@@ -826,7 +971,7 @@ extern "C" int mmdit_gemm_bf16(const mmdit_gemm_args* a, void* stream_) {
   // split-K GEMMs (explicit slices / fp32 accumulate) fill the machine through the split, not through
   // narrower tiles: the split planners (here and ops._plan_split) assume 128x256 tiles
   const bool will_split = a->split_k > 1 || (a->split_k <= 0 && a->accumulate && a->d_fp32 && a->K >= 8 * BLOCK_K);
-  p.block_n = (swiglu || qknorm) ? 256 : a->force_block_n ? a->force_block_n
+  p.block_n = (swiglu || qknorm || swiglu_bwd) ? 256 : a->force_block_n ? a->force_block_n
               : (will_split && a->N > 128) ? 256 : pick_block_n(a->M, a->N, sms);
   MMDIT_REQUIRE(p.block_n == 64 || p.block_n == 128 || p.block_n == 256, MMDIT_ERR_ARG,
                 "gemm: block_n %d", p.block_n);
@@ -836,10 +981,11 @@ extern "C" int mmdit_gemm_bf16(const mmdit_gemm_args* a, void* stream_) {
     const char* e = getenv("MMDIT_GEMM_PAIR");
     env_pair = e ? atoi(e) : 1;
   }
-  const bool pair = swiglu || qknorm || (env_pair && p.block_n == 256 && a->M > BLOCK_M && !(a->reserved & 16));
+  const bool pair = swiglu || qknorm || swiglu_bwd || (env_pair && p.block_n == 256 && a->M > BLOCK_M && !(a->reserved & 16));
   const int workers = pair ? sms / 2 : sms;  // persistent work units running concurrently
   const int stage_bytes = A_STAGE_BYTES + (pair ? p.block_n / 2 : p.block_n) * BLOCK_K * 2;
-  p.stages = (SMEM_BUDGET - 1024 - BAR_BYTES - EPI_STAGE_BYTES) / stage_bytes;
+  const int epi_bytes = swiglu_bwd ? EPI_STAGE_BYTES_SWIGLU_BWD : EPI_STAGE_BYTES;
+  p.stages = (SMEM_BUDGET - 1024 - BAR_BYTES - epi_bytes) / stage_bytes;
   if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
   {
     static int env_stages = -1;  // perf experiments: MMDIT_GEMM_STAGES caps the smem ring depth
@@ -908,7 +1054,7 @@ extern "C" int mmdit_gemm_bf16(const mmdit_gemm_args* a, void* stream_) {
     if (rc) return rc;
   }
 
-  const int smem_bytes = p.stages * stage_bytes + EPI_STAGE_BYTES + BAR_BYTES + 1024;
+  const int smem_bytes = p.stages * stage_bytes + epi_bytes + BAR_BYTES + 1024;
   const int total_work = tiles * p.split_k;
   const int grid = pair ? 2 * (total_work < workers ? total_work : workers)
                         : (total_work < sms ? total_work : sms);
@@ -921,6 +1067,9 @@ extern "C" int mmdit_gemm_bf16(const mmdit_gemm_args* a, void* stream_) {
   int ev = EV_GENERIC;
   if (swiglu) {
     ev = EV_SWIGLU_TMA;
+  } else if (swiglu_bwd) {
+    ev = EV_SWIGLU_BWD;
+    p.colsum_partial = static_cast<float*>(a->colsum_partial);
   } else if (qknorm) {
     ev = EV_QKNORM_TMA;
     p.qk_wq = static_cast<const float*>(a->qk_wq);
@@ -953,13 +1102,13 @@ extern "C" int mmdit_gemm_bf16(const mmdit_gemm_args* a, void* stream_) {
   }
   MMDIT_REQUIRE(p.slice_stride == 0 || ev == EV_F32, MMDIT_ERR_ALIGN,
                 "gemm: split-K slices mode needs N %% 8 == 0 and 16-byte aligned D");
-  if (ev == EV_BF16_TMA || ev == EV_SWIGLU_TMA || ev == EV_QKNORM_TMA) {
-    uint64_t dims[2] = {(uint64_t)(swiglu ? a->N / 2 : a->N), (uint64_t)a->M}, strides[1] = {(uint64_t)a->ldd * 2};
+  if (ev == EV_BF16_TMA || ev == EV_SWIGLU_TMA || ev == EV_QKNORM_TMA || ev == EV_SWIGLU_BWD) {
+    uint64_t dims[2] = {(uint64_t)(swiglu ? a->N / 2 : swiglu_bwd ? 2 * a->N : a->N), (uint64_t)a->M}, strides[1] = {(uint64_t)a->ldd * 2};
     uint32_t box[2] = {64, 32};
     int rc_d = encode_tmap(&p.tmD, a->D, 2, dims, strides, box, 2, true);
     if (rc_d) return rc_d;
-    if (swiglu || qknorm) {
-      dims[0] = (uint64_t)(qknorm ? a->N / 3 * 2 : a->N);
+    if (swiglu || qknorm || swiglu_bwd) {
+      dims[0] = (uint64_t)(qknorm ? a->N / 3 * 2 : swiglu_bwd ? 2 * a->N : a->N);
       strides[0] = (uint64_t)a->ld_aux * 2;
       rc_d = encode_tmap(&p.tmAux, a->aux, 2, dims, strides, box, 2, true);
       if (rc_d) return rc_d;
@@ -981,6 +1130,9 @@ extern "C" int mmdit_gemm_bf16(const mmdit_gemm_args* a, void* stream_) {
     LAUNCH_EV(EV_BF16_TMA)
     case EV_SWIGLU_TMA:
       rc = launch_variant<EV_SWIGLU_TMA, true>(grid, smem_bytes, stream, p);
+      break;
+    case EV_SWIGLU_BWD:
+      rc = launch_variant<EV_SWIGLU_BWD, true>(grid, smem_bytes, stream, p);
       break;
     case EV_QKNORM_TMA:
       rc = launch_variant<EV_QKNORM_TMA, true>(grid, smem_bytes, stream, p);

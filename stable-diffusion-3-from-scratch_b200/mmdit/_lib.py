@@ -33,6 +33,7 @@ class GemmArgs(C.Structure):
         ("force_block_n", c_i32), ("reserved", c_i32),
         ("qk_wq", c_vp), ("qk_wk", c_vp), ("rope_cos", c_vp), ("rope_sin", c_vp),
         ("qk_tokens", c_i32), ("qk_eps", c_f32),
+        ("colsum_partial", c_vp),
     ]
 
 
@@ -54,7 +55,7 @@ class AttnArgs(C.Structure):
     ]
 
 
-EPI_NONE, EPI_GATE_RESID, EPI_SILU, EPI_RESID, EPI_SWIGLU, EPI_QKNORM = 0, 1, 2, 3, 4, 5
+EPI_NONE, EPI_GATE_RESID, EPI_SILU, EPI_RESID, EPI_SWIGLU, EPI_QKNORM, EPI_SWIGLU_BWD = 0, 1, 2, 3, 4, 5, 6
 
 _lib = None
 

@@ -25,6 +25,43 @@ FUSED_SWIGLU = os.environ.get("MMDIT_FUSED_SWIGLU", "1") == "1"
 # MMDIT_FUSED_QKNORM=1 (experimental, not yet validated on hardware): per-head RMSNorm + 2-D RoPE of
 # q and k in the epilogue of the packed q|k|v projection (QKVProjFn / JointAttentionPreNormFn below)
 FUSED_QKNORM = os.environ.get("MMDIT_FUSED_QKNORM", "0") == "1"
+# MMDIT_FUSED_SWIGLU_BWD=1: the SwiGLU backward runs in the epilogue of w3's data-gradient GEMM
+FUSED_SWIGLU_BWD = os.environ.get("MMDIT_FUSED_SWIGLU_BWD", "0") == "1"
+
+
+class _SwigluLink:
+    """Shared by a SwiGLUHiddenFn node and the gated-linear node (w3) that consumes its output, so that
+    the w3 data-gradient GEMM can apply the SwiGLU backward in its epilogue (ops.gemm_swiglu_bwd).
+    The w3 node hands dh12 back through this object; the gradient it returns for the activation is a
+    correctly shaped view of dh12 that SwiGLUHiddenFn.backward recognises by its address and ignores."""
+    __slots__ = ("h12", "has_bias", "paired", "dh12", "db", "dummy_ptr")
+
+    def __init__(self, h12, has_bias):
+        self.h12, self.has_bias, self.paired = h12, has_bias, False
+        self.dh12 = self.db = self.dummy_ptr = None
+
+
+_SWIGLU_LINKS = {}   # data_ptr of a SwiGLU activation -> its link, until the consumer's forward claims it
+
+
+def _claim_swiglu_link(a):
+    link = _SWIGLU_LINKS.pop(a.data_ptr(), None) if _SWIGLU_LINKS else None
+    if link is not None:
+        link.paired = True
+    return link
+
+
+def _w3_dgrad(link, da, wb):
+    """dL/d(input of w3): plain GEMM, or -- when the input is a SwiGLU activation -- the fused GEMM that
+    already yields dh12 (returned to the SwiGLU node through the link; the caller gets a dummy view)."""
+    if link is None:
+        return ops.gemm(da, wb, b_major=1)
+    hid = wb.shape[1]
+    link.db = torch.zeros(2 * hid, device=da.device, dtype=F32) if link.has_bias else None
+    link.dh12 = ops.gemm_swiglu_bwd(da, wb, link.h12, link.db)
+    dummy = link.dh12[:, :hid]
+    link.dummy_ptr = dummy.data_ptr()
+    return dummy
 
 
 def _wgrad_slot(params):
@@ -130,6 +167,7 @@ class GatedLinearFn(Function):
             aux = ops.gemm(a, wb, bias=bb)
             o = ops.gate_residual_fwd(aux, gate, resid, rows_per_batch)
         ctx.save_for_backward(a, wb, aux, gate)
+        ctx.link = _claim_swiglu_link(a)
         ctx.wparam = w
         ctx.rpb = rows_per_batch
         ctx.has_bias = b is not None
@@ -144,7 +182,7 @@ class GatedLinearFn(Function):
         dgate = torch.empty((Bn, n), device=do.device, dtype=BF16)       # written by the kernel
         dab = torch.empty((Bn, n), device=do.device, dtype=F32) if ctx.has_bias else None
         da = ops.gate_bwd(do, aux, gate, dgate, dab, rpb)
-        dx = ops.gemm(da, wb, b_major=1)
+        dx = _w3_dgrad(ctx.link, da, wb)
         dw = _wgrad_gemm(da, a, [ctx.wparam]).view(ctx.wparam.shape)
         db = dab.sum(0) if ctx.has_bias else None
         return dx, None, None, dgate, do, None, dw, db
@@ -161,6 +199,7 @@ class GatedLinearLNFn(Function):
         aux = ops.gemm(a, wb, bias=bb)
         xo, y, mean, rstd = ops.gate_residual_ln_fwd(aux, gate, resid, shift, scale, rows_per_batch)
         ctx.save_for_backward(a, wb, aux, gate, xo, mean, rstd, scale)
+        ctx.link = _claim_swiglu_link(a)
         ctx.wparam = w
         ctx.rpb = rows_per_batch
         ctx.has_bias = b is not None
@@ -182,7 +221,7 @@ class GatedLinearLNFn(Function):
         dgate = torch.empty((Bn, n), device=do.device, dtype=BF16)
         dab = torch.empty((Bn, n), device=do.device, dtype=F32) if ctx.has_bias else None
         da = ops.gate_bwd(do, aux, gate, dgate, dab, rpb)
-        dx = ops.gemm(da, wb, b_major=1)
+        dx = _w3_dgrad(ctx.link, da, wb)
         dw = _wgrad_gemm(da, a, [ctx.wparam]).view(ctx.wparam.shape)
         db = dab.sum(0) if ctx.has_bias else None
         return (dx, None, None, dgate, do, None if dmod is None else dmod[0],
@@ -429,14 +468,28 @@ class SwiGLUHiddenFn(Function):
         ctx.save_for_backward(x2, wb, h12)
         ctx.wparam = w12
         ctx.meta = (x.shape, b12 is not None)
+        ctx.link = None
+        if (FUSED_SWIGLU_BWD and any(ctx.needs_input_grad) and a.is_contiguous()
+                and ops.swiglu_bwd_fusable(a.shape[0], a.shape[1])):
+            if len(_SWIGLU_LINKS) > 8:
+                _SWIGLU_LINKS.clear()     # activations nobody claimed (hidden() used on its own)
+            ctx.link = _SWIGLU_LINKS[a.data_ptr()] = _SwigluLink(h12, b12 is not None)
         return a.reshape(*x.shape[:-1], a.shape[-1])
 
     @staticmethod
     def backward(ctx, da):
         x2, wb, h12 = ctx.saved_tensors
         xshape, has_bias = ctx.meta
-        db = torch.zeros(h12.shape[1], device=da.device, dtype=F32) if has_bias else None
-        dh = ops.swiglu_bwd(da.reshape(-1, da.shape[-1]).contiguous(), h12, db)
+        link = ctx.link
+        if link is not None and link.paired:
+            # the w3 node already applied the SwiGLU backward in its GEMM epilogue; `da` is its dummy view
+            if link.dh12 is None or da.data_ptr() != link.dummy_ptr:
+                raise RuntimeError("fused SwiGLU backward: the activation must feed exactly one w3 GEMM")
+            dh, db = link.dh12, link.db
+            link.dh12 = link.db = link.h12 = None
+        else:
+            db = torch.zeros(h12.shape[1], device=da.device, dtype=F32) if has_bias else None
+            dh = ops.swiglu_bwd(da.reshape(-1, da.shape[-1]).contiguous(), h12, db)
         dx = ops.gemm(dh, wb, b_major=1).reshape(xshape)
         dw = _wgrad_gemm(dh, x2, [ctx.wparam])
         return dx, None, dw, db

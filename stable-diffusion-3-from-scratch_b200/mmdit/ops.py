@@ -10,7 +10,8 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import EPI_GATE_RESID, EPI_NONE, EPI_QKNORM, EPI_RESID, EPI_SILU, EPI_SWIGLU  # noqa: F401
+from ._lib import (EPI_GATE_RESID, EPI_NONE, EPI_QKNORM, EPI_RESID, EPI_SILU, EPI_SWIGLU,  # noqa: F401
+                   EPI_SWIGLU_BWD)
 
 BF16 = torch.bfloat16
 F32 = torch.float32
@@ -151,6 +152,41 @@ def _gemm(A, B, *, a_major=0, b_major=0, out=None, out_dtype=BF16, accumulate=Fa
     fn = L.mmdit_gemm_bf16_simt if simt else L.mmdit_gemm_bf16
     _lib.check(fn(C.byref(a), _s()), "mmdit_gemm_bf16")
     return out
+
+
+def swiglu_bwd_fusable(rows, hidden):
+    """Shapes the fused w3-dgrad + SwiGLU-backward GEMM accepts (whole 128-row / 256-column tiles)."""
+    return rows > 128 and rows % 128 == 0 and hidden % 256 == 0
+
+
+def gemm_swiglu_bwd(dy, w3b, h12, db12, debug=0):
+    """dh12 [R, 2*hidden] = SwiGLU backward of (dy @ W3) against the saved pre-activations h12 = [x1 | x2],
+    in the epilogue of the data-gradient GEMM of w3 (w3b: bf16 [d, hidden]); the activation gradient is
+    never materialised.  db12 (fp32 [2*hidden], zero-initialised by the caller, or None) receives the
+    column sums of dh12 (the w12 bias gradient).  Bit-identical to gemm(b_major=1) + swiglu_bwd."""
+    _need_cuda(dy, w3b, h12)
+    _rowmajor2d(dy, "dy")
+    R, d = dy.shape
+    hid = w3b.shape[1]
+    assert w3b.shape[0] == d and h12.shape == (R, 2 * hid) and h12.is_contiguous() and swiglu_bwd_fusable(R, hid)
+    dh12 = torch.empty_like(h12)
+    a = _lib.GemmArgs()
+    a.A, a.B, a.D = dy.data_ptr(), w3b.data_ptr(), dh12.data_ptr()
+    a.M, a.N, a.K = R, hid, d
+    a.lda, a.ldb, a.ldd = dy.stride(0), w3b.stride(0), dh12.stride(0)
+    a.a_major, a.b_major = 0, 1
+    a.epilogue = EPI_SWIGLU_BWD
+    a.reserved = int(debug)
+    a.aux, a.ld_aux = h12.data_ptr(), h12.stride(0)
+    part = None
+    if db12 is not None:
+        part = torch.empty((R // 32, 2 * hid), device=dy.device, dtype=F32)
+        a.colsum_partial = part.data_ptr()
+    _lib.check(_lib.lib().mmdit_gemm_bf16(C.byref(a), _s()), "mmdit_gemm_bf16 (SwiGLU backward)")
+    if part is not None:
+        _lib.check(_lib.lib().mmdit_fold_rows_f32(_p(part), _p(db12), R // 32, 2 * hid, 2 * hid, _s()),
+                   "mmdit_fold_rows_f32")
+    return dh12
 
 
 # ---------------------------------------------------------------- attention

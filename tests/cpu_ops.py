@@ -152,6 +152,14 @@ def attn_bwd(q, k, v, o, lse, d_o, dq, dk, dv, B, H, N, M, scale):
     return acc
 
 
+def swiglu_bwd_fusable(rows, hidden):
+    return rows > 128 and rows % 128 == 0 and hidden % 256 == 0
+
+
+def gemm_swiglu_bwd(dy, w3b, h12, db12):
+    return swiglu_bwd(gemm(dy, w3b, b_major=1), h12, db12)
+
+
 # ------------------------------------------------------------------- row kernels
 def _ln_mod(x, shift, scale, rpb):
     one_plus = (1 + scale.detach().to(BF16)).float() + (scale - scale.detach())   # bf16-rounded value, unit grad

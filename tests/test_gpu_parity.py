@@ -29,6 +29,7 @@ def test_gemm_all_layouts_and_epilogues(dev):
     assert gemm_probe.group_major()
     assert gemm_probe.group_epi()
     assert gemm_probe.group_swiglu()      # fused SwiGLU epilogue == GEMM + activation kernel, bit for bit
+    assert gemm_probe.group_swiglu_bwd()  # w3 dgrad with the SwiGLU backward in its epilogue == two kernels, bit for bit
 
 
 def test_rowwise_kernels(dev):

@@ -11,7 +11,7 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "stable-diffusion-3-from-scratch_b200"))
-from mmdit import _lib  # noqa: E402
+from mmdit import _lib, ops  # noqa: E402
 
 L = _lib.lib()
 dev = "cuda"
@@ -233,6 +233,70 @@ def group_qknorm():
     return ok
 
 
+def group_swiglu_bwd():
+    """w3 data-gradient GEMM with the SwiGLU backward in its epilogue vs the two-kernel path (bit-identical
+    dh12, bias-gradient column sums), and both timed under a CUDA graph."""
+    ok = True
+    for (R, d, hid) in [(512, 256, 1024), (1280, 384, 768), (16384, 768, 3072), (9856, 768, 3072), (16384, 1536, 6144)]:
+        g = torch.Generator(device=dev).manual_seed(R + d)
+        dy = (0.5 * torch.randn(R, d, device=dev, generator=g)).bfloat16()
+        w3 = (torch.randn(d, hid, device=dev, generator=g) / d ** 0.5).bfloat16()
+        h12 = torch.randn(R, 2 * hid, device=dev, generator=g).bfloat16()
+        db_f = torch.zeros(2 * hid, device=dev)
+        dh_f = ops.gemm_swiglu_bwd(dy, w3, h12, db_f)
+        da = ops.gemm(dy, w3, b_major=1)
+        db_u = torch.zeros(2 * hid, device=dev)
+        dh_u = ops.swiglu_bwd(da, h12, db_u)
+        torch.cuda.synchronize()
+        ndiff = int((dh_f.view(torch.int16) != dh_u.view(torch.int16)).sum())
+        rel_db = float((db_f - db_u).abs().max() / db_u.abs().max())
+        nob = ops.gemm_swiglu_bwd(dy, w3, h12, None)
+        same_nob = bool(torch.equal(nob, dh_f))
+        if ndiff:
+            bad = torch.nonzero(dh_f.view(torch.int16) != dh_u.view(torch.int16))
+            rows = bad[:, 0].unique()
+            print("    bad rows", rows[:12].tolist(), "n_rows", rows.numel(), "cols of first row",
+                  bad[bad[:, 0] == rows[0], 1].tolist()[:40])
+            r, c = int(bad[0, 0]), int(bad[0, 1])
+            print("    first bad: fused", float(dh_f[r, c]), "unfused", float(dh_u[r, c]), "row%128", r % 128, "col%64", c % 64, "half", c // hid)
+            again = ops.gemm_swiglu_bwd(dy, w3, h12, torch.zeros_like(db_f))
+            print("    fused run twice identical:", bool(torch.equal(again, dh_f)),
+                  " second run vs unfused:", int((again.view(torch.int16) != dh_u.view(torch.int16)).sum()))
+        if R >= 8192 and os.environ.get("SWIGLU_BWD_DEBUG"):
+            for dbg in (0,):
+                bad_runs = []
+                for rep in range(4):
+                    out = ops.gemm_swiglu_bwd(dy, w3, h12, None, debug=dbg)
+                    bad_runs.append(int((out.view(torch.int16) != dh_u.view(torch.int16)).sum()))
+                print(f"    debug={dbg:3d}: mismatches per run {bad_runs}")
+        good = ndiff == 0 and rel_db < 2e-3 and same_nob
+        ok &= good
+        print(f"[swiglu_bwd R={R} d={d} hid={hid}] differing dh12 elements: {ndiff} of {dh_f.numel()}, "
+              f"db max-rel {rel_db:.2e}, without column sums identical: {same_nob}  {'ok' if good else 'FAIL'}")
+        if R >= 8192:
+            def timeit(fn, n=8):
+                fn(); torch.cuda.synchronize()
+                gr = torch.cuda.CUDAGraph()
+                st = torch.cuda.Stream()
+                with torch.cuda.stream(st):
+                    with torch.cuda.graph(gr, stream=st):
+                        for _ in range(n):
+                            fn()
+                gr.replay(); torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(5):
+                    gr.replay()
+                e1.record(); torch.cuda.synchronize()
+                return e0.elapsed_time(e1) / (5 * n) * 1e3
+            dbz = torch.zeros(2 * hid, device=dev)
+            t_f = timeit(lambda: ops.gemm_swiglu_bwd(dy, w3, h12, dbz))
+            t_g = timeit(lambda: ops.gemm(dy, w3, b_major=1))
+            t_s = timeit(lambda: ops.swiglu_bwd(da, h12, dbz))
+            print(f"    fused {t_f:7.1f} us   vs   GEMM {t_g:6.1f} + swiglu_bwd {t_s:6.1f} = {t_g + t_s:6.1f} us")
+    return ok
+
+
 def group_perf():
     shapes = [
         ("qkv_x cfg2", 16384, 2304, 768, 0, 0, False),
@@ -282,6 +346,6 @@ if __name__ == "__main__":
     g = sys.argv[1] if len(sys.argv) > 1 else "basic"
     _lib.check(L.mmdit_device_check(), "device_check")
     t0 = time.time()
-    ok = {"basic": group_basic, "major": group_major, "epi": group_epi, "perf": group_perf, "swiglu": group_swiglu, "qknorm": group_qknorm}[g]()
+    ok = {"basic": group_basic, "major": group_major, "epi": group_epi, "perf": group_perf, "swiglu": group_swiglu, "qknorm": group_qknorm, "swiglu_bwd": group_swiglu_bwd}[g]()
     print(f"GROUP {g}: {'ALL PASS' if ok else 'SOME FAIL'} ({time.time() - t0:.1f}s)")
     sys.exit(0 if ok else 1)

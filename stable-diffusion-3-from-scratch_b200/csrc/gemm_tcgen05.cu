@@ -26,6 +26,7 @@ constexpr int BLOCK_K = 64;
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KiB
 constexpr int MAX_STAGES = 8;
 constexpr int GEMM_THREADS = 256;
+constexpr int GEMM_THREADS_SWIGLU_BWD = 384;  // 8 epilogue warps: two per TMEM lane quarter, 32 columns of a chunk each
 constexpr int SMEM_BUDGET = 227 * 1024;
 constexpr int BAR_BYTES = 256;
 constexpr int EPI_STAGE_BYTES = 4 * 32 * 64 * 4;  // 4 warps x (32 rows x 64 fp32)
@@ -160,11 +161,16 @@ enum { EV_GENERIC = 0, EV_BF16 = 1, EV_BF16_BIAS = 2, EV_GATE = 3, EV_F32 = 4, E
 // itself), each thread reads its row from the swizzled tiles, computes d1 / d2 from the bf16-rounded
 // accumulator exactly as swiglu_bwd_kernel does, and the two output tiles leave by TMA stores; the
 // column sums of the strip (w12 bias gradient) are read back from the output tiles, two columns per lane.
-// Validated bit-identical to gemm + swiglu_bwd (tools/gemm_probe.py swiglu_bwd); alone it saves 12-66 us per
-// GEMM, inside the cfg2 step nothing (the 4 epilogue warps need ~2.4x the mainloop time per tile), so
-// the trainer keeps the two kernels unless MMDIT_FUSED_SWIGLU_BWD=1.  Two hazards found on hardware are
-// written down at the places they bit: the x tiles must be double-buffered, and the output tiles need a
-// bar.sync (not __syncwarp) between the st.shared and the TMA store.
+// Validated bit-identical to gemm + swiglu_bwd (tools/gemm_probe.py swiglu_bwd).  Eight epilogue warps (two
+// per TMEM lane quarter, 32 columns of every chunk each, sharing the quarter's tiles) instead of four changed
+// little (142 -> 134 us at the cfg2 image shape against 57 + 95 us for the two kernels): the fused kernel
+// moves 430 MB (h12 in, dh12 out) with one 8 KB prefetch in flight per lane quarter, i.e. it is bound by
+// bytes in flight (Little: 32 KB x 148 SMs / ~1.5 us = 3.2 TB/s, the measured rate), and a deeper x-tile
+// ring does not fit next to a 4-stage operand ring.  Inside the cfg2 step it buys nothing (the separate
+// swiglu_bwd overlaps the other stream's GEMMs), so the trainer keeps the two kernels unless
+// MMDIT_FUSED_SWIGLU_BWD=1.  Two hazards found on hardware are written down where they bit: the x tiles
+// must be double-buffered, and the output tiles need a bar.sync (not __syncwarp) between the st.shared
+// and the TMA store.
 // EV_QKNORM_TMA (experimental, MMDIT_FUSED_QKNORM=1; NOT yet validated on hardware): the packed
 // q|k|v projection writes the raw projection (D, needed by the backward) and, for the q and k
 // columns, the per-head RMSNorm * weight followed by the 2-D RoPE rotation (aux = [M, 2d]) --
@@ -277,7 +283,7 @@ __device__ __forceinline__ void epilogue_fast(const GemmParams& p, const float* 
 // traffic (L2 -> smem) instead of 48 KB for the same FLOPs -- the single-CTA 128x256 tile is
 // L2-bandwidth bound at ~2/3 of the MMA rate on B200 (profiles/r01_gemm_shapes_*.log).
 template <int EV, bool PAIR>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__(EV == EV_SWIGLU_BWD ? GEMM_THREADS_SWIGLU_BWD : GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   // 128B-swizzled tiles need 1024 B alignment in the shared window.
@@ -318,7 +324,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
-      mbar_init(&tmem_empty[s], PAIR ? 8 : 4);  // one arrive per epilogue warp (of both CTAs)
+      mbar_init(&tmem_empty[s], (PAIR ? 8 : 4) * (EV == EV_SWIGLU_BWD ? 2 : 1));  // one arrive per epilogue warp (of both CTAs)
     }
     if constexpr (EV == EV_SWIGLU_BWD)
       for (int w = 0; w < 8; ++w) mbar_init(&epi_in[w], 1);
@@ -435,14 +441,15 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
     }
   } else if (warp >= 4) {
     // ---------------------------------------------------------------- epilogue
-    const int ew = warp - 4;  // == warp % 4 -> TMEM lane quarter
+    const int ew = (warp - 4) & 3;  // == warp % 4 -> TMEM lane quarter
+    [[maybe_unused]] const int hw = (warp - 4) >> 2;  // EV_SWIGLU_BWD: which 32-column half of every chunk (8 epilogue warps)
     int as = 0;
     uint32_t aphase = 0;
     const uint32_t leader_tmem_empty = PAIR ? mapa_u32(smem_u32(&tmem_empty[0]), 0) : 0u;
     [[maybe_unused]] int tma_buf = 0;
     [[maybe_unused]] uint32_t epi_q = 0;   // EV_SWIGLU_BWD: chunks processed so far (x-tile buffer = q & 1)
     if constexpr (EV == EV_SWIGLU_BWD) {
-      if (unit0 < total_work && elect_one()) {   // x1 / x2 tiles of this warp's first chunk
+      if (hw == 0 && unit0 < total_work && elect_one()) {   // x1 / x2 tiles of this lane quarter's first chunk
         const int tile0 = unit0 / p.split_k;
         const long long mf = static_cast<long long>(PAIR ? (tile0 % p.tiles_m) * 2 + (int)rank : tile0 % p.tiles_m) * BLOCK_M + ew * 32;
         const int nf = (tile0 / p.tiles_m) * 256;
@@ -648,7 +655,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
               m_next = static_cast<long long>(PAIR ? (tile2 % p.tiles_m) * 2 + (int)rank : tile2 % p.tiles_m) * BLOCK_M + ew * 32;
               n_next = (tile2 / p.tiles_m) * 256;
             }
-            if (has_next && elect_one()) {
+            if (hw == 0 && has_next && elect_one()) {
               uint64_t* nb = &epi_in[2 * ew + (buf ^ 1)];
               uint8_t* nx = wbase + (buf ^ 1) * 8192;
               mbar_expect_tx(nb, 2 * 4096);
@@ -657,9 +664,8 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
             }
             __syncwarp();
           }
-          uint32_t r0[32], r1[32];
-          tmem_ld32(taddr + c * 64, r0);
-          tmem_ld32(taddr + c * 64 + 32, r1);
+          uint32_t r0[32];
+          tmem_ld32(taddr + c * 64 + hw * 32, r0);
           tmem_ld_wait();
           if (c == 3) {  // accumulator drained: hand the TMEM stage back
             tc_fence_before();
@@ -669,60 +675,61 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
               else mbar_arrive(&tmem_empty[as]);
             }
           }
-          // this thread's row of the x1 / x2 tiles (128B-swizzled, as TMA wrote them)
+          // this thread's half row of the x1 / x2 tiles (128B-swizzled, as TMA wrote them)
           mbar_wait(&epi_in[2 * ew + buf], (epi_q >> 1) & 1u);
-          uint32_t x1p[32], x2p[32];
+          uint32_t x1p[16], x2p[16];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const uint4 u = *reinterpret_cast<const uint4*>(tX1 + lane * 128 + ((j ^ (lane & 7)) << 4));
-            const uint4 v = *reinterpret_cast<const uint4*>(tX2 + lane * 128 + ((j ^ (lane & 7)) << 4));
+          for (int j = 0; j < 4; ++j) {
+            const int jj = hw * 4 + j;
+            const uint4 u = *reinterpret_cast<const uint4*>(tX1 + lane * 128 + ((jj ^ (lane & 7)) << 4));
+            const uint4 v = *reinterpret_cast<const uint4*>(tX2 + lane * 128 + ((jj ^ (lane & 7)) << 4));
             x1p[4 * j] = u.x; x1p[4 * j + 1] = u.y; x1p[4 * j + 2] = u.z; x1p[4 * j + 3] = u.w;
             x2p[4 * j] = v.x; x2p[4 * j + 1] = v.y; x2p[4 * j + 2] = v.z; x2p[4 * j + 3] = v.w;
           }
           // d1 = g x2 sg (1 + x1 (1 - sg)),  d2 = g x1 sg   with g rounded to bf16 (as the unfused path stores it)
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const uint32_t* src = j < 16 ? &r0[2 * j] : &r1[2 * (j - 16)];
-            const float g0 = __bfloat162float(__float2bfloat16(__uint_as_float(src[0])));
-            const float g1 = __bfloat162float(__float2bfloat16(__uint_as_float(src[1])));
+          for (int j = 0; j < 16; ++j) {
+            const float g0 = __bfloat162float(__float2bfloat16(__uint_as_float(r0[2 * j])));
+            const float g1 = __bfloat162float(__float2bfloat16(__uint_as_float(r0[2 * j + 1])));
             const float2 a = unpack_bf16x2(x1p[j]), b = unpack_bf16x2(x2p[j]);
             const float s0 = __fdividef(1.f, 1.f + __expf(-a.x)), s1 = __fdividef(1.f, 1.f + __expf(-a.y));
             x1p[j] = pack_bf16x2(g0 * b.x * s0 * (1.f + a.x * (1.f - s0)), g1 * b.y * s1 * (1.f + a.y * (1.f - s1)));
             x2p[j] = pack_bf16x2(g0 * (a.x * s0), g1 * (a.y * s1));
           }
-          if (elect_one()) tma_wait_group_read0();   // the previous chunk's stores have read the output tiles
-          __syncwarp();
+          // the previous chunk's stores (issued by the hw == 0 warp) have read the output tiles
+          if (hw == 0 && elect_one()) tma_wait_group_read0();
+          named_bar_sync(8 + ew, 64);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            *reinterpret_cast<uint4*>(tD1 + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+          for (int j = 0; j < 4; ++j) {
+            const int jj = hw * 4 + j;
+            *reinterpret_cast<uint4*>(tD1 + lane * 128 + ((jj ^ (lane & 7)) << 4)) =
                 make_uint4(x1p[4 * j], x1p[4 * j + 1], x1p[4 * j + 2], x1p[4 * j + 3]);
-            *reinterpret_cast<uint4*>(tD2 + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+            *reinterpret_cast<uint4*>(tD2 + lane * 128 + ((jj ^ (lane & 7)) << 4)) =
                 make_uint4(x2p[4 * j], x2p[4 * j + 1], x2p[4 * j + 2], x2p[4 * j + 3]);
           }
           fence_proxy_async_smem();
-          // bar.sync (not bar.warp.sync): it also drains this warp's pending st.shared.  With __syncwarp the
-          // store below occasionally read a tile whose LAST 16-byte chunk of a few rows was still the
-          // previous chunk's (single-buffered tiles leave no slack; seen as ~1e-6 of the elements).
-          named_bar_sync(8 + ew, 32);
-          if (!(p.debug & 1) && elect_one()) {
+          // bar.sync over the two warps of the lane quarter (it also drains their pending st.shared: with a
+          // plain __syncwarp the store below occasionally read a tile whose last 16-byte chunk of a few rows
+          // was still the previous chunk's -- single-buffered output tiles leave no slack)
+          named_bar_sync(8 + ew, 64);
+          if (hw == 0 && !(p.debug & 1) && elect_one()) {
             tma_store_2d(&p.tmD, tD1, n, static_cast<int>(m0));
             tma_store_2d(&p.tmD, tD2, hid + n, static_cast<int>(m0));
             tma_commit_group();
           }
           __syncwarp();   // reconverge before the next chunk's warp-collective tcgen05.ld
-          if (p.colsum_partial) {   // column sums of this 32-row strip: lane l owns columns 2l, 2l+1 of the chunk
-            float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
-            const int wofs = (lane & 3) * 4, jch = lane >> 2;
+          if (p.colsum_partial) {   // column sums of this 32-row strip: lane l owns column 32 hw + l of the chunk
+            float a0 = 0.f, b0 = 0.f;
+            const int jch = hw * 4 + (lane >> 3), bofs = (lane & 7) * 2;
 #pragma unroll 8
             for (int r = 0; r < 32; ++r) {
-              const int off = r * 128 + ((jch ^ (r & 7)) << 4) + wofs;
-              const float2 u = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(tD1 + off));
-              const float2 v = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(tD2 + off));
-              a0 += u.x; a1 += u.y; b0 += v.x; b1 += v.y;
+              const int off = r * 128 + ((jch ^ (r & 7)) << 4) + bofs;
+              a0 += __bfloat162float(*reinterpret_cast<const bf16*>(tD1 + off));
+              b0 += __bfloat162float(*reinterpret_cast<const bf16*>(tD2 + off));
             }
-            float* dst = p.colsum_partial + (m0 >> 5) * (2LL * hid) + n + 2 * lane;
-            *reinterpret_cast<float2*>(dst) = make_float2(a0, a1);
-            *reinterpret_cast<float2*>(dst + hid) = make_float2(b0, b1);
+            float* dst = p.colsum_partial + (m0 >> 5) * (2LL * hid) + n + hw * 32 + lane;
+            dst[0] = a0;
+            dst[hid] = b0;
           }
         }
       } else if constexpr (EV == EV_BF16_TMA) {
@@ -881,7 +888,7 @@ static int launch_variant(int grid, int smem_bytes, cudaStream_t stream, const G
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.blockDim = dim3(EV == EV_SWIGLU_BWD ? GEMM_THREADS_SWIGLU_BWD : GEMM_THREADS);
     cfg.dynamicSmemBytes = smem_bytes;
     cfg.stream = stream;
     cudaLaunchAttribute at[2];

@@ -416,9 +416,9 @@ def run_product(args):
     if args.config == "cfg2":
         # NOT measured in this run (DRAM counters need ncu): the committed capture of this same step
         try:
-            with open(os.path.join(ROOT, "profiles", "r01_kernel_metrics_v6.json")) as f:
+            with open(os.path.join(ROOT, "profiles", "r02_kernel_metrics.json")) as f:
                 traffic = json.load(f)["gemm_tcgen05_kernel"]["dram_bytes_per_launch"]
-            traffic_src = ("constant from profiles/r01_kernel_metrics_v6.json (ncu dram__bytes_read+write, mean over "
+            traffic_src = ("constant from profiles/r02_kernel_metrics.json (ncu dram__bytes_read+write, mean over "
                            "the cfg2 step's GEMM launches); not re-measured by bench.py")
         except Exception:  # noqa: BLE001
             pass

@@ -119,7 +119,7 @@ class Transformer_Block_Dual(nn.Module):
         """(LN-mod(X'), X') with X' = resid + gate * lin(a): the out-projection's gated residual and the
         LayerNorm-modulate in front of the MLP share one pass over the GEMM output."""
         # above 1024 columns the one-pass kernel holds too many registers (one 8-warp block per SM:
-        # 106 us vs 30 + 31 us for the two kernels at d = 1536, profiles/r02_rowpipe_experiment.md)
+        # 106 us vs 30 + 31 us for the two kernels at d = 1536, profiles/r02_experiments_not_shipped.md)
         if not Fn.FUSED_GATE_LN or resid.shape[-1] > 1024:
             return modulate_keep(self._gated(a, lin, gate, resid, rows_per_batch), shift, scale)
         wb = packed_weight(lin, "w", [lin.weight])

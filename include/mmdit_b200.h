@@ -55,7 +55,7 @@ enum {
   MMDIT_EPI_SILU = 2,      /* D = silu(acc+bias)                                */
   MMDIT_EPI_RESID = 3,     /* D = acc + bias + resid                            */
   MMDIT_EPI_SWIGLU = 4,    /* B = [gate rows; up rows] (xformers w12, MLP.py:19): D[M,N/2] = silu(g)*u,
-                              aux[M,N] = acc+bias (bf16, required); needs N % 256 == 0, M > 128 */
+                              aux[M,N] = acc+bias (bf16; NULL = not kept, inference); needs N % 256 == 0, M > 128 */
   MMDIT_EPI_QKNORM = 5,    /* B = [q; k; v] rows (N = 3d): D[M,N] = acc (+bias), aux[M,2d] = per-head
                               RMSNorm * weight (+ 2-D RoPE) of the q and k columns (Attention.py:61-64,
                               130-134,174-194); validated, measured slower than the separate kernel */

@@ -623,8 +623,10 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
             }
           }
           if (m0 >= p.M) continue;
-          stage_tile(gq, &p.tmAux, n);
-          stage_tile(uq, &p.tmAux, p.swiglu_half + n);
+          if (p.aux) {   // the pre-activation is only kept for the backward (inference passes aux = NULL)
+            stage_tile(gq, &p.tmAux, n);
+            stage_tile(uq, &p.tmAux, p.swiglu_half + n);
+          }
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const float2 g = unpack_bf16x2(gq[j]), u = unpack_bf16x2(uq[j]);
@@ -940,12 +942,12 @@ extern "C" int mmdit_gemm_bf16(const mmdit_gemm_args* a, void* stream_) {
   const bool swiglu = a->epilogue == MMDIT_EPI_SWIGLU;
   if (swiglu) {
     auto al = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
-    MMDIT_REQUIRE(a->aux && !a->d_fp32 && !a->accumulate && a->split_k <= 1 && a->remap_rows == 0 &&
+    MMDIT_REQUIRE(!a->d_fp32 && !a->accumulate && a->split_k <= 1 && a->remap_rows == 0 &&
                       a->b_major == 0 && a->N % 256 == 0 && a->M > BLOCK_M && al(a->D) && al(a->aux) &&
                       a->ldd % 8 == 0 && a->ld_aux % 8 == 0 && (!a->bias || (a->bias_fp32 && al(a->bias))),
                   MMDIT_ERR_UNSUPPORTED,
-                  "gemm: the SwiGLU epilogue needs aux, bf16 D [M,N/2], K-major B, N %% 256 == 0, M > 128, "
-                  "16-byte aligned rows and an fp32 bias");
+                  "gemm: the SwiGLU epilogue needs bf16 D [M,N/2] (and aux [M,N] unless NULL = inference), "
+                  "K-major B, N %% 256 == 0, M > 128, 16-byte aligned rows and an fp32 bias");
   }
   const bool swiglu_bwd = a->epilogue == MMDIT_EPI_SWIGLU_BWD;
   if (swiglu_bwd) {
@@ -1114,7 +1116,7 @@ extern "C" int mmdit_gemm_bf16(const mmdit_gemm_args* a, void* stream_) {
     uint32_t box[2] = {64, 32};
     int rc_d = encode_tmap(&p.tmD, a->D, 2, dims, strides, box, 2, true);
     if (rc_d) return rc_d;
-    if (swiglu || qknorm || swiglu_bwd) {
+    if ((swiglu && a->aux) || qknorm || swiglu_bwd) {
       dims[0] = (uint64_t)(qknorm ? a->N / 3 * 2 : swiglu_bwd ? 2 * a->N : a->N);
       strides[0] = (uint64_t)a->ld_aux * 2;
       rc_d = encode_tmap(&p.tmAux, a->aux, 2, dims, strides, box, 2, true);

@@ -460,7 +460,10 @@ class SwiGLUHiddenFn(Function):
         if FUSED_SWIGLU and x2.shape[0] > 128 and wb.shape[0] % 256 == 0 and (bias is None or bias.dtype == F32):
             # activation in the GEMM epilogue: the [R, 8d] pre-activation is written once (for the
             # backward) and never re-read by a separate activation kernel
-            h12 = torch.empty((x2.shape[0], wb.shape[0]), device=x.device, dtype=BF16)
+            # (inference: nobody reads the pre-activation -- the epilogue skips its two stores per chunk,
+            #  2/3 of this GEMM's output bytes)
+            h12 = (torch.empty((x2.shape[0], wb.shape[0]), device=x.device, dtype=BF16)
+                   if any(ctx.needs_input_grad) else None)
             a = ops.gemm(x2, wb, bias=bias, epilogue=ops.EPI_SWIGLU, aux=h12)
         else:
             h12 = ops.gemm(x2, wb, bias=bias)

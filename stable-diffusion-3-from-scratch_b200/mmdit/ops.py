@@ -108,8 +108,6 @@ def _gemm(A, B, *, a_major=0, b_major=0, out=None, out_dtype=BF16, accumulate=Fa
             return out
     if dst is not None:
         out = dst
-    if epilogue == EPI_SWIGLU and aux is None:
-        raise ValueError("gemm: the SwiGLU epilogue needs aux (the [M, N] pre-activation output)")
     if out is None:
         rows = out_rows if out_rows is not None else M
         if remap is not None and out_rows is None:

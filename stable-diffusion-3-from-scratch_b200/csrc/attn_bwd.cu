@@ -62,12 +62,7 @@ __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, 
                : "memory");
 }
 
-// PT_TMEM (experimental, MMDIT_ATTN_BWD_PT_TMEM=1; NOT yet validated on hardware): P^T is kept
-// in tensor memory (the 64 columns the other accumulators leave free) and feeds the dV MMA as a
-// TMEM A operand, instead of going through shared memory.  The timeline in
-// profiles/r01_attention_timeline_notes.md shows the kernel shared-memory-bandwidth bound; this
-// removes 32 KB of stores and 32 KB of MMA operand reads per 128x128 tile.
-template <bool PT_TMEM>
+// First generation (one CTA per item); kept as the MMDIT_ATTN_BWD_V2=0 fallback.
 __global__ void __launch_bounds__(BWD_THREADS, 1)
 attn_bwd_kernel(const __grid_constant__ AttnBwdParams p) {
   // (no early pdl_trigger: dependents are released when this grid exits)
@@ -93,7 +88,6 @@ attn_bwd_kernel(const __grid_constant__ AttnBwdParams p) {
   uint64_t* all_done = bars + 11; // every MMA of this CTA has retired
   uint64_t* stage_free = bars + 12;  // [2]: dQ staging (aliases the P^T buffer) read out by the TMA reduce
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
-  [[maybe_unused]] uint64_t* dv_done = bars + 15;  // PT_TMEM: the dV MMAs reading P^T from TMEM have retired
   uint64_t* st_free = bars + 16;  // 256: every compute thread holds its S^T / dP^T values in registers
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -130,7 +124,6 @@ attn_bwd_kernel(const __grid_constant__ AttnBwdParams p) {
       mbar_init(all_done, 1);
       mbar_init(&stage_free[0], 1);
       mbar_init(&stage_free[1], 1);
-      if constexpr (PT_TMEM) mbar_init(dv_done, 1);
       mbar_fence_init();
       // K, V and the first two (Q, dO) tiles fly while TMEM is being allocated
       mbar_expect_tx(kv_full, 2 * ATT_TILE_BYTES);
@@ -154,7 +147,6 @@ attn_bwd_kernel(const __grid_constant__ AttnBwdParams p) {
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tm_St = tmem_base, tm_dPt = tmem_base + 128, tm_dV = tmem_base + 256,
                  tm_dK = tmem_base + 320, tm_dQ = tmem_base + 384;
-  [[maybe_unused]] const uint32_t tm_Pt = tmem_base + 448;   // PT_TMEM: bf16 P^T, 128 lanes x 64 columns
 
   if (warp == 0) {
     if (lane == 0) {
@@ -223,16 +215,9 @@ attn_bwd_kernel(const __grid_constant__ AttnBwdParams p) {
         tc_fence_after();
         TL(tls++, 30 + i);
         if (elect_one()) {
-          if constexpr (PT_TMEM) {
-            for (int k = 0; k < nq / 16; ++k)
-              umma_bf16_ts(tm_dV, tm_Pt + k * 8, do_desc0_mn + st * kTile + k * kStepMN, id_kn,
-                           (i > 0 || k > 0) ? 1u : 0u);
-            umma_commit(dv_done);   // P^T in TMEM may be overwritten once these retire
-          } else {
-            for (int k = 0; k < nq / 16; ++k)
-              umma_bf16(tm_dV, pt_desc + (k >> 2) * kTile + (k & 3) * kStepK,
-                        do_desc0_mn + st * kTile + k * kStepMN, id_kn, (i > 0 || k > 0) ? 1u : 0u);
-          }
+          for (int k = 0; k < nq / 16; ++k)
+            umma_bf16(tm_dV, pt_desc + (k >> 2) * kTile + (k & 3) * kStepK,
+                      do_desc0_mn + st * kTile + k * kStepMN, id_kn, (i > 0 || k > 0) ? 1u : 0u);
           for (int k = 0; k < nq / 16; ++k)
             umma_bf16(tm_dK, dst_desc + (k >> 2) * kTile + (k & 3) * kStepK,
                       q_desc0_mn + st * kTile + k * kStepMN, id_kn, (i > 0 || k > 0) ? 1u : 0u);
@@ -346,18 +331,13 @@ attn_bwd_kernel(const __grid_constant__ AttnBwdParams p) {
       uint8_t* bufP = sPt + (i & 1) * 2 * ATT_TILE_BYTES;
       uint8_t* bufD = sdSt + (i & 1) * 2 * ATT_TILE_BYTES;
       const int nq = (q_valid + 15) & ~15;
-      [[maybe_unused]] uint32_t ppk[32];   // PT_TMEM: this thread's 64 P^T values as packed bf16 pairs
-      if constexpr (PT_TMEM) {
-#pragma unroll
-        for (int q = 0; q < 32; ++q) ppk[q] = 0u;
-      }
       // chunks of 32 query columns this thread will load from TMEM (warp-uniform)
       const int n_ld = (quarter * 32 >= k_valid) ? 0 : (hf * 64 >= nq ? 0 : (hf * 64 + 32 >= nq ? 1 : 2));
       if (n_ld == 0) {
         tc_fence_before();
         mbar_arrive(st_free);
       }
-#pragma unroll(PT_TMEM ? 2 : 1)
+#pragma unroll 1
       for (int c = 0; c < 2; ++c) {
         if (hf * 64 + c * 32 >= nq) break;  // warp-uniform: these query columns do not exist
         if (quarter * 32 >= k_valid) {
@@ -368,7 +348,7 @@ attn_bwd_kernel(const __grid_constant__ AttnBwdParams p) {
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             const int off = ((c * 4 + g) ^ (r & 7)) << 4;
-            if constexpr (!PT_TMEM) *reinterpret_cast<uint4*>(prow + off) = make_uint4(0u, 0u, 0u, 0u);
+            *reinterpret_cast<uint4*>(prow + off) = make_uint4(0u, 0u, 0u, 0u);
             *reinterpret_cast<uint4*>(drow + off) = make_uint4(0u, 0u, 0u, 0u);
           }
           continue;
@@ -405,23 +385,8 @@ attn_bwd_kernel(const __grid_constant__ AttnBwdParams p) {
           w.x = pack_bf16x2(de[0], de[1]); w.y = pack_bf16x2(de[2], de[3]);
           w.z = pack_bf16x2(de[4], de[5]); w.w = pack_bf16x2(de[6], de[7]);
           const int off = ((c * 4 + g) ^ (r & 7)) << 4;
-          if constexpr (PT_TMEM) {
-            ppk[c * 16 + g * 4] = u.x; ppk[c * 16 + g * 4 + 1] = u.y;
-            ppk[c * 16 + g * 4 + 2] = u.z; ppk[c * 16 + g * 4 + 3] = u.w;
-          } else {
-            *reinterpret_cast<uint4*>(prow + off) = u;
-          }
+          *reinterpret_cast<uint4*>(prow + off) = u;
           *reinterpret_cast<uint4*>(drow + off) = w;
-        }
-      }
-      if constexpr (PT_TMEM) {
-        if (hf * 64 < nq) {   // this warp's 64 query columns (or their first half) exist
-          if (i > 0) {
-            mbar_wait(dv_done, (i - 1) & 1);   // the previous tile's dV MMAs no longer read P^T
-            tc_fence_after();
-          }
-          tmem_st32(tm_Pt + lane_off + hf * 32, ppk);
-          tmem_st_wait();
         }
       }
       fence_proxy_async_smem();
@@ -1038,16 +1003,8 @@ extern "C" int mmdit_attn_bwd(const mmdit_attn_args* a, void* stream_) {
   p.B = a->B; p.H = a->H; p.N = a->N; p.M = a->M;
   p.scale = a->scale;
   p.scale_log2 = a->scale * 1.4426950408889634f;
-  static const int pt_tmem = [] {   // variant validated on hardware (round 2): correct, no faster -> off
-    const char* ev = getenv("MMDIT_ATTN_BWD_PT_TMEM");
-    return ev ? atoi(ev) : 0;
-  }();
-  static const cudaError_t attr_rc = [] {   // thread-safe one-time initialisation (C++11 magic static)
-    cudaError_t r = cudaFuncSetAttribute(attn_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM);
-    if (r == cudaSuccess)
-      r = cudaFuncSetAttribute(attn_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM);
-    return r;
-  }();
+  static const cudaError_t attr_rc =   // thread-safe one-time initialisation (C++11 magic static)
+      cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM);
   if (attr_rc != cudaSuccess) {
     set_last_error("attn_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(attr_rc));
     return (int)attr_rc;
@@ -1069,8 +1026,7 @@ extern "C" int mmdit_attn_bwd(const mmdit_attn_args* a, void* stream_) {
     launch_k(attn_bwd2_kernel, dim3(grid2), dim3(BWD_THREADS), BWD2_SMEM, stream, p, items);
   } else {
     dim3 grid(nt, a->H, a->B);
-    if (pt_tmem) launch_k(attn_bwd_kernel<true>, grid, dim3(BWD_THREADS), BWD_SMEM, stream, p);
-    else launch_k(attn_bwd_kernel<false>, grid, dim3(BWD_THREADS), BWD_SMEM, stream, p);
+    launch_k(attn_bwd_kernel, grid, dim3(BWD_THREADS), BWD_SMEM, stream, p);
   }
   rc = check_launch("attn_bwd_kernel");
   if (rc) return rc;

@@ -179,6 +179,12 @@ int mmdit_gate_bwd(const void* dout, const void* a, const void* gate, void* da, 
                    int32_t dgate_bf16, float* dab, float* workspace, int64_t rows, int32_t d,
                    int64_t rows_per_batch, int64_t ld_gate, int64_t ld_dgate, int64_t ld_dab,
                    void* stream);
+/* Which generation of the row kernels (LayerNorm-modulate fwd / bwd, gated residual + LN, gate bwd,
+ * QK-RMSNorm + RoPE fwd / bwd) the entry points above and below launch: 2 (default; csrc/rowwise2.cu,
+ * csrc/qknorm2.cu) or 1 (csrc/rowwise.cu, csrc/elementwise.cu; also what shapes the second generation
+ * does not cover fall back to).  Same results (forward kernels bit-identical); the environment variable
+ * MMDIT_ROW_KERNELS=1 sets the initial value.  Not a reference interface: an A/B and regression knob. */
+int mmdit_set_row_kernel_generation(int32_t generation);
 
 /* Text front-end (diff_model.py:168-172,323-326): out = bf16(sigma * RMSNorm_fp32(c) * w).
  * Tokens [0,split) of each sample use (w1,sigma1) -> out1 [B*split, d]; tokens [split,M)

@@ -51,6 +51,31 @@ void prefer_max_smem_carveout(const void* kernel);
     (void)once_;                                                                          \
   } while (0)
 
+// ---- second-generation row kernels (rowwise2.cu / qknorm2.cu) ------------------------------
+// row_kernel_generation(): 2 unless MMDIT_ROW_KERNELS=1 or mmdit_set_row_kernel_generation(1).
+// Each *_v2 launcher returns ROW_V2_UNSUPPORTED when the shape stays on the first generation.
+constexpr int ROW_V2_UNSUPPORTED = -1000;
+int row_kernel_generation();
+int ln_modulate_fwd_v2(const void* x, const void* shift, const void* scale, void* y, float* mean, float* rstd,
+                       long long rows, int d, long long rows_per_batch, long long ld_mod, float eps,
+                       cudaStream_t stream);
+int gate_residual_ln_fwd_v2(const void* a, const void* gate, const void* resid, const void* shift,
+                            const void* scale, void* x_out, void* y, float* mean, float* rstd, long long rows,
+                            int d, long long rows_per_batch, long long ld_gate, long long ld_mod, float eps,
+                            cudaStream_t stream);
+int ln_modulate_bwd_v2(const void* dy, const void* x, const float* mean, const float* rstd, const void* scale,
+                       const void* dres, void* dx, float* workspace, long long rows, int d,
+                       long long rows_per_batch, long long ld_mod, int* bpb_out, cudaStream_t stream);
+int gate_bwd_v2(const void* dout, const void* a, const void* gate, void* da, float* workspace, long long rows,
+                int d, long long rows_per_batch, long long ld_gate, int* bpb_out, cudaStream_t stream);
+int qknorm_rope_fwd_v2(const void* qkv, const float* wq, const float* wk, const float* rope_cos,
+                       const float* rope_sin, void* out, long long rows, int d, long long ld_in,
+                       long long ld_out, int T, float eps, cudaStream_t stream);
+int qknorm_rope_bwd_v2(const float* dq_acc, int acc_tokens, int acc_tok_off, const void* dqk, const void* qkv,
+                       const float* wq, const float* wk, const float* rope_cos, const float* rope_sin,
+                       void* dqkv, float* dwq, float* dwk, long long rows, int d, long long ld_g,
+                       long long ld_in, long long ld_dout, int T, float eps, cudaStream_t stream);
+
 // ---------------------------------------------------------------- launch ---
 // Programmatic dependent launch: a kernel launched through launch_k() may be scheduled while the
 // previous kernel of its stream is still running (as soon as every CTA of that kernel has executed
@@ -408,6 +433,43 @@ __device__ __forceinline__ float warp_max(float v) {
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
 }
+// ---- packed fp32x2 (FADD2 / FMUL2 / FFMA2: one issue slot, two columns) ---------------------
+// ptxas may still contract a mul.f32x2 feeding an add into one FFMA2 / FFMA.
+__device__ __forceinline__ unsigned long long f2_bits(float2 v) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(v.x), "f"(v.y));
+  return r;
+}
+__device__ __forceinline__ float2 f2_from(unsigned long long r) {
+  float2 v;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(v.x), "=f"(v.y) : "l"(r));
+  return v;
+}
+__device__ __forceinline__ float2 f2_fma(float2 a, float2 b, float2 c) {
+  unsigned long long r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(f2_bits(a)), "l"(f2_bits(b)), "l"(f2_bits(c)));
+  return f2_from(r);
+}
+__device__ __forceinline__ float2 f2_mul(float2 a, float2 b) {
+  unsigned long long r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(f2_bits(a)), "l"(f2_bits(b)));
+  return f2_from(r);
+}
+__device__ __forceinline__ float2 f2_add(float2 a, float2 b) {
+  unsigned long long r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(f2_bits(a)), "l"(f2_bits(b)));
+  return f2_from(r);
+}
+__device__ __forceinline__ float2 f2_dup(float v) { return make_float2(v, v); }
+// bf16x2 word -> two floats (exact): low half = element 2p, high half = element 2p + 1
+__device__ __forceinline__ float2 bf2_unpack(uint32_t u) {
+  return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
+}
+__device__ __forceinline__ uint32_t bf2_pack(float2 v) { return pack_bf16x2(v.x, v.y); }
+__device__ __forceinline__ uint32_t word(const uint4& u, int p) {
+  return p == 0 ? u.x : p == 1 ? u.y : p == 2 ? u.z : u.w;
+}
+
 // x * sigmoid(x); fast reciprocal (MUFU.RCP + FMUL, ~2 ulp): every consumer rounds to bf16 anyway,
 // and the IEEE division sequence is ~3x the instructions inside the 4-warp GEMM epilogues.
 __device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.f + __expf(-x)); }

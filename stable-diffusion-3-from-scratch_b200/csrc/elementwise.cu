@@ -570,6 +570,11 @@ int mmdit_qknorm_rope_fwd(const void* qkv, const float* wq, const float* wk, con
   MMDIT_REQUIRE(qkv && wq && wk && out && rows > 0 && d > 0 && d % 64 == 0 && ld_in % 8 == 0 &&
                     ld_out % 8 == 0 && tokens_per_sample > 0 && (!rope_cos == !rope_sin),
                 MMDIT_ERR_ARG, "qknorm_rope_fwd: bad arguments (head_dim is fixed at 64)");
+  if (row_kernel_generation() >= 2) {
+    const int rc = qknorm_rope_fwd_v2(qkv, wq, wk, rope_cos, rope_sin, out, rows, d, ld_in, ld_out,
+                                      tokens_per_sample, eps, (cudaStream_t)stream);
+    if (rc != ROW_V2_UNSUPPORTED) return rc;
+  }
   const long long work = rows * (long long)(d / 8);
   MMDIT_CARVEOUT(qknorm_rope_fwd_kernel);
   launch_k(qknorm_rope_fwd_kernel, dim3(grid_for(work, 256)), dim3(256), 0, (cudaStream_t)stream, 
@@ -594,6 +599,11 @@ int mmdit_qknorm_rope_bwd(const void* dqk, const void* qkv, const float* wq, con
   MMDIT_REQUIRE(dqk && qkv && wq && wk && dqkv && dwq && dwk && rows > 0 && d % 64 == 0 &&
                     ld_g % 8 == 0 && ld_in % 8 == 0 && ld_dout % 8 == 0 && tokens_per_sample > 0,
                 MMDIT_ERR_ARG, "qknorm_rope_bwd: bad arguments");
+  if (row_kernel_generation() >= 2) {
+    const int rc = qknorm_rope_bwd_v2(nullptr, 0, 0, dqk, qkv, wq, wk, rope_cos, rope_sin, dqkv, dwq, dwk, rows, d,
+                                      ld_g, ld_in, ld_dout, tokens_per_sample, eps, (cudaStream_t)stream);
+    if (rc != ROW_V2_UNSUPPORTED) return rc;
+  }
   const long long work = rows * (long long)(d / 8);
   unsigned grid = grid_for(work, 256);
   const unsigned cap = (unsigned)num_sms() * qkn_cap();  // fewer, longer-lived blocks: fewer atomics
@@ -615,6 +625,12 @@ int mmdit_qknorm_rope_bwd_acc(const float* dq_acc, int32_t acc_tokens, int32_t a
                     acc_tok_off >= 0 && acc_tok_off + tokens_per_sample <= acc_tokens &&
                     rows % tokens_per_sample == 0,
                 MMDIT_ERR_ARG, "qknorm_rope_bwd_acc: bad arguments");
+  if (row_kernel_generation() >= 2) {
+    const int rc = qknorm_rope_bwd_v2(dq_acc, acc_tokens, acc_tok_off, dqk, qkv, wq, wk, rope_cos, rope_sin, dqkv,
+                                      dwq, dwk, rows, d, ld_g, ld_in, ld_dout, tokens_per_sample, eps,
+                                      (cudaStream_t)stream);
+    if (rc != ROW_V2_UNSUPPORTED) return rc;
+  }
   const long long work = rows * (long long)(d / 8);
   unsigned grid = grid_for(work, 256);
   const unsigned cap = (unsigned)num_sms() * qkn_cap();  // fewer, longer-lived blocks: fewer atomics

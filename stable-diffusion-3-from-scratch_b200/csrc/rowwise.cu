@@ -491,6 +491,11 @@ int mmdit_ln_modulate_fwd(const void* x, const void* shift, const void* scale, v
                           int64_t ld_mod, float eps, void* stream) {
   MMDIT_REQUIRE(x && shift && scale && y && rows > 0 && d > 0 && d % 8 == 0 && rows_per_batch > 0,
                 MMDIT_ERR_ARG, "ln_modulate_fwd: bad arguments (d must be a multiple of 8)");
+  if (row_kernel_generation() >= 2) {
+    const int rc = ln_modulate_fwd_v2(x, shift, scale, y, mean, rstd, rows, d, rows_per_batch, ld_mod, eps,
+                                      (cudaStream_t)stream);
+    if (rc != ROW_V2_UNSUPPORTED) return rc;
+  }
   const unsigned grid = (unsigned)((rows + ROW_WARPS - 1) / ROW_WARPS);
   DISPATCH_NC(d, MMDIT_CARVEOUT(ln_mod_fwd_kernel<NC>); (launch_k(ln_mod_fwd_kernel<NC>, grid, dim3(ROW_THREADS), 0, (cudaStream_t)stream, 
                      (const bf16*)x, (const bf16*)shift, (const bf16*)scale, (bf16*)y, mean, rstd,
@@ -505,6 +510,11 @@ int mmdit_gate_residual_ln_fwd(const void* a, const void* gate, const void* resi
   MMDIT_REQUIRE(a && gate && resid && shift && scale && x_out && y && rows > 0 && d > 0 && d % 8 == 0 &&
                     rows_per_batch > 0 && ld_gate % 8 == 0 && ld_mod % 8 == 0,
                 MMDIT_ERR_ARG, "gate_residual_ln_fwd: bad arguments (d, ld_gate, ld_mod must be multiples of 8)");
+  if (row_kernel_generation() >= 2) {
+    const int rc = gate_residual_ln_fwd_v2(a, gate, resid, shift, scale, x_out, y, mean, rstd, rows, d,
+                                           rows_per_batch, ld_gate, ld_mod, eps, (cudaStream_t)stream);
+    if (rc != ROW_V2_UNSUPPORTED) return rc;
+  }
   const unsigned grid = (unsigned)((rows + ROW_WARPS - 1) / ROW_WARPS);
   DISPATCH_NC(d, MMDIT_CARVEOUT(gate_res_ln_fwd_kernel<NC>); (launch_k(gate_res_ln_fwd_kernel<NC>, grid, dim3(ROW_THREADS), 0, (cudaStream_t)stream, 
                      (const bf16*)a, (const bf16*)gate, (const bf16*)resid, (const bf16*)shift,
@@ -553,13 +563,21 @@ int mmdit_ln_modulate_bwd(const void* dy, const void* x, const float* mean, cons
   const int nb = (int)(rows / rows_per_batch);
   const size_t smem = (size_t)BWD_WARPS * 2 * d * sizeof(float);
   MMDIT_REQUIRE(smem <= 48 * 1024, MMDIT_ERR_UNSUPPORTED, "ln_modulate_bwd: d=%d too wide", d);
-  int rpb = 16;
-  DISPATCH_NC(d, rpb = rows_per_block((const void*)ln_mod_bwd_kernel<NC>, smem, rows_per_batch, nb));
-  const int bpb = (int)((rows_per_batch + rpb - 1) / rpb);
-  const unsigned grid = (unsigned)(nb * bpb);
-  DISPATCH_NC(d, MMDIT_CARVEOUT(ln_mod_bwd_kernel<NC>); (launch_k(ln_mod_bwd_kernel<NC>, grid, dim3(BWD_THREADS), smem, (cudaStream_t)stream, 
-                     (const bf16*)dy, (const bf16*)x, mean, rstd, (const bf16*)scale,
-                     (const bf16*)dres, (bf16*)dx, workspace, d, rows_per_batch, ld_mod, rpb, bpb)));
+  int bpb = 0, v2 = ROW_V2_UNSUPPORTED;
+  if (row_kernel_generation() >= 2)
+    v2 = ln_modulate_bwd_v2(dy, x, mean, rstd, scale, dres, dx, workspace, rows, d, rows_per_batch, ld_mod, &bpb,
+                            (cudaStream_t)stream);
+  if (v2 == ROW_V2_UNSUPPORTED) {
+    int rpb = 16;
+    DISPATCH_NC(d, rpb = rows_per_block((const void*)ln_mod_bwd_kernel<NC>, smem, rows_per_batch, nb));
+    bpb = (int)((rows_per_batch + rpb - 1) / rpb);
+    const unsigned grid = (unsigned)(nb * bpb);
+    DISPATCH_NC(d, MMDIT_CARVEOUT(ln_mod_bwd_kernel<NC>); (launch_k(ln_mod_bwd_kernel<NC>, grid, dim3(BWD_THREADS), smem, (cudaStream_t)stream,
+                       (const bf16*)dy, (const bf16*)x, mean, rstd, (const bf16*)scale,
+                       (const bf16*)dres, (bf16*)dx, workspace, d, rows_per_batch, ld_mod, rpb, bpb)));
+  } else if (v2 != MMDIT_OK) {
+    return v2;
+  }
   dim3 g2((2 * d + 255) / 256, nb);
   MMDIT_CARVEOUT(fold_batch_partials_kernel);
   launch_k(fold_batch_partials_kernel, g2, dim3(256), 0, (cudaStream_t)stream, workspace, dshift, dscale, d, bpb,
@@ -577,13 +595,20 @@ int mmdit_gate_bwd(const void* dout, const void* a, const void* gate, void* da, 
   const int nb = (int)(rows / rows_per_batch);
   const size_t smem = (size_t)BWD_WARPS * 2 * d * sizeof(float);
   MMDIT_REQUIRE(smem <= 48 * 1024, MMDIT_ERR_UNSUPPORTED, "gate_bwd: d=%d too wide", d);
-  int rpb = 16;
-  DISPATCH_NC(d, rpb = rows_per_block((const void*)gate_bwd_kernel<NC>, smem, rows_per_batch, nb));
-  const int bpb = (int)((rows_per_batch + rpb - 1) / rpb);
-  const unsigned grid = (unsigned)(nb * bpb);
-  DISPATCH_NC(d, MMDIT_CARVEOUT(gate_bwd_kernel<NC>); (launch_k(gate_bwd_kernel<NC>, grid, dim3(BWD_THREADS), smem, (cudaStream_t)stream, 
-                     (const bf16*)dout, (const bf16*)a, (const bf16*)gate, (bf16*)da, workspace, d,
-                     rows_per_batch, ld_gate, rpb, bpb)));
+  int bpb = 0, v2 = ROW_V2_UNSUPPORTED;
+  if (row_kernel_generation() >= 2)
+    v2 = gate_bwd_v2(dout, a, gate, da, workspace, rows, d, rows_per_batch, ld_gate, &bpb, (cudaStream_t)stream);
+  if (v2 == ROW_V2_UNSUPPORTED) {
+    int rpb = 16;
+    DISPATCH_NC(d, rpb = rows_per_block((const void*)gate_bwd_kernel<NC>, smem, rows_per_batch, nb));
+    bpb = (int)((rows_per_batch + rpb - 1) / rpb);
+    const unsigned grid = (unsigned)(nb * bpb);
+    DISPATCH_NC(d, MMDIT_CARVEOUT(gate_bwd_kernel<NC>); (launch_k(gate_bwd_kernel<NC>, grid, dim3(BWD_THREADS), smem, (cudaStream_t)stream,
+                       (const bf16*)dout, (const bf16*)a, (const bf16*)gate, (bf16*)da, workspace, d,
+                       rows_per_batch, ld_gate, rpb, bpb)));
+  } else if (v2 != MMDIT_OK) {
+    return v2;
+  }
   dim3 g2((2 * d + 255) / 256, nb);
   launch_k(fold_batch_partials_kernel, g2, dim3(256), 0, (cudaStream_t)stream, workspace, dgate, dab, d, bpb,
                                                                   ld_dgate, ld_dab, dgate_bf16, 0);

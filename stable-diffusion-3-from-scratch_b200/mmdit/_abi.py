@@ -49,6 +49,7 @@ SIGNATURES = {
     "mmdit_comm_close": [vp],
     "mmdit_allreduce_mean_f32": [vp, i64, i64, i32, vp],
     "mmdit_rowreduce_workspace_floats": [i64, i32, i64],
+    "mmdit_set_row_kernel_generation": [i32],
     "mmdit_swiglu_bwd_workspace_floats": [i64, i32],
 }
 

@@ -251,6 +251,11 @@ def attn_bwd(q, k, v, o, lse, d_o, dq, dk, dv, B, H, N, M, scale):
 
 
 # ------------------------------------------------------------- row kernels
+def set_row_kernel_generation(generation):
+    """2 (default): csrc/rowwise2.cu + csrc/qknorm2.cu; 1: the first-generation kernels (A/B and regression knob)."""
+    _lib.check(_lib.lib().mmdit_set_row_kernel_generation(int(generation)), "mmdit_set_row_kernel_generation")
+
+
 def ln_modulate_fwd(x, shift, scale, rows_per_batch, save_stats=True):
     """x [R,d] bf16; shift/scale [B,d] bf16 views (same row stride)."""
     _need_cuda(x)

@@ -1,6 +1,7 @@
-"""GB/s table of the LayerNorm-modulate / gate row kernels at the shapes the train step runs them at
-(CUDA-graph replay over rotating buffer sets larger than the L2), plus a bit-for-bit check of the fused
-gate+residual+LN forward against the two kernels it replaces.
+"""GB/s table of the LayerNorm-modulate / gate / QK-norm row kernels at the shapes the train step runs them
+at (CUDA-graph replay over rotating buffer sets larger than the L2), both kernel generations side by side;
+a bit-for-bit check of the fused gate+residual+LN forward against the two kernels it replaces; and every
+second-generation kernel against its first-generation counterpart on the same inputs.
 python tools/row_probe.py [check|perf|all]   (exit code 1 on any mismatch)"""
 import os
 import sys
@@ -32,6 +33,95 @@ def same(got, ref, tag):
     n = int((got.view(torch.int16) != ref.view(torch.int16)).sum()) if got.dtype == BF else int((got != ref).sum())
     print(f"    {tag:34s} differing elements: {n} of {got.numel()}")
     return n
+
+
+def close_bf16(got, ref, tag, exact):
+    """second generation vs first: bit-identical where the operation order is the same (forward kernels), else
+    at most one bf16 ulp apart on at most 1 % of the elements (ptxas contracts a few mul + add pairs)"""
+    global ok_all
+    g, r = got.float(), ref.float()
+    diff = (g - r).abs()
+    n = int((diff > 0).sum())
+    ulp = torch.maximum(g.abs(), r.abs()) * 2.0 ** -7 + 1e-30
+    worst = float((diff / ulp).max()) if n else 0.0
+    if exact:
+        bad = n != 0
+    elif got.dtype == BF:
+        bad = worst > 1.001 or n > 1e-2 * got.numel()
+    else:
+        bad = float(diff.max()) > 2e-5 * float(r.abs().max()) + 1e-12
+    ok_all &= not bad
+    print(f"    {tag:34s} differing: {n} of {got.numel()} (worst {worst:.2f} bf16 ulp) {'FAIL' if bad else 'ok'}")
+
+
+def both_generations(fn):
+    ops.set_row_kernel_generation(1)
+    a = fn()
+    ops.set_row_kernel_generation(2)
+    b = fn()
+    return a, b
+
+
+def check_generations(Bn, T, d):
+    """every second-generation row kernel against the first-generation one on the same inputs"""
+    print(f"[gen 2 vs gen 1] B={Bn} rows/sample={T} d={d}")
+    t = make(Bn, T, d, seed=3)
+    a, resid, gate, shift, scale, dy, dres = (t[k] for k in ("a", "resid", "gate", "shift", "scale", "dy", "dres"))
+    (y1, m1, r1), (y2, m2, r2) = both_generations(lambda: ops.ln_modulate_fwd(a, shift, scale, T))
+    close_bf16(y2, y1, "ln_modulate_fwd y", True)
+    close_bf16(m2, m1, "ln_modulate_fwd mean", True)
+    close_bf16(r2, r1, "ln_modulate_fwd rstd", True)
+    if d <= 1024:
+        f1, f2 = both_generations(lambda: ops.gate_residual_ln_fwd(a, gate, resid, shift, scale, T))
+        for k, nm in enumerate(("x'", "y", "mean", "rstd")):
+            close_bf16(f2[k], f1[k], f"gate_residual_ln_fwd {nm}", True)
+
+    def lnb():
+        dmod = torch.zeros(2, Bn, d, device=dev, dtype=BF)
+        dx = ops.ln_modulate_bwd(dy, a, m1, r1, scale, dres, dmod[0], dmod[1], T)
+        dmod32 = torch.zeros(2, Bn, d, device=dev)
+        dx0 = ops.ln_modulate_bwd(dy, a, m1, r1, scale, None, dmod32[0], dmod32[1], T)
+        return dx, dmod, dx0, dmod32
+    b1, b2 = both_generations(lnb)
+    for k, nm in enumerate(("dx (+dres)", "dshift/dscale bf16", "dx (no dres)", "dshift/dscale fp32")):
+        close_bf16(b2[k], b1[k], f"ln_modulate_bwd {nm}", False)
+
+    def gb():
+        dgate = torch.zeros(Bn, d, device=dev, dtype=BF)
+        dab = torch.zeros(Bn, d, device=dev)
+        da = ops.gate_bwd(dy, a, gate, dgate, dab, T)
+        return da, dgate, dab
+    g1, g2 = both_generations(gb)
+    for k, nm in enumerate(("da", "dgate", "dab")):
+        close_bf16(g2[k], g1[k], f"gate_bwd {nm}", nm == "da")
+
+    if d % 64 == 0:
+        g = torch.Generator(device=dev).manual_seed(11)
+        R = Bn * T
+        qkv = torch.randn(R, 3 * d, device=dev, generator=g).bfloat16()
+        dqk = torch.randn(R, 2 * d, device=dev, generator=g).bfloat16()
+        wq, wk = torch.rand(64, device=dev, generator=g) + 0.5, torch.rand(64, device=dev, generator=g) + 0.5
+        ang = torch.rand(T, 32, device=dev, generator=g) * 6.0
+        for rope in ((torch.cos(ang).contiguous(), torch.sin(ang).contiguous()), None):
+            tag = "rope" if rope else "text"
+            o1, o2 = both_generations(lambda: ops.qknorm_rope_fwd(qkv, wq, wk, rope, d, T))
+            close_bf16(o2, o1, f"qknorm_rope_fwd ({tag})", True)
+
+            def qb(acc):
+                dqkv = torch.zeros(R, 3 * d, device=dev, dtype=BF)
+                dw = torch.zeros(2, 64, device=dev)
+                if acc:
+                    pad = 5
+                    dq_acc = torch.zeros(Bn, T + 2 * pad, d, device=dev)
+                    dq_acc[:, pad:pad + T] = dqk[:, :d].float().view(Bn, T, d)
+                    ops.qknorm_rope_bwd(dqk, qkv, wq, wk, rope, dqkv, dw[0], dw[1], d, T, dq_acc=dq_acc, acc_off=pad)
+                else:
+                    ops.qknorm_rope_bwd(dqk, qkv, wq, wk, rope, dqkv, dw[0], dw[1], d, T)
+                return dqkv[:, :2 * d], dw
+            for acc in (False, True):
+                q1, q2 = both_generations(lambda: qb(acc))
+                close_bf16(q2[0], q1[0], f"qknorm_rope_bwd ({tag}{', fp32 dq' if acc else ''}) dqk", False)
+                close_bf16(q2[1], q1[1], f"qknorm_rope_bwd ({tag}{', fp32 dq' if acc else ''}) dw", False)
 
 
 def make(Bn, T, d, seed=0):
@@ -97,8 +187,11 @@ def perf(name, Bn, T, d):
     rows = []
 
     def add(tag, nbytes, fn):
-        us = timeit(fn, nbuf)
-        rows.append((tag, us, nbytes / us / 1e3))
+        us = []
+        for gen in (1, 2):
+            ops.set_row_kernel_generation(gen)
+            us.append(timeit(fn, nbuf))
+        rows.append((tag, us, [nbytes / u / 1e3 for u in us]))
 
     S = lambda i: sets[i]
     add("gate_residual_fwd", 3 * per, lambda i: ops.gate_residual_fwd(S(i)["a"], S(i)["gate"], S(i)["resid"], T))
@@ -133,8 +226,10 @@ def perf(name, Bn, T, d):
         S(i)["dqk"], S(i)["qkv"], wq, wk, rope, S(i)["dqkv"], S(i)["dw"][0], S(i)["dw"][1], d, T, dq_acc=S(i)["dq_acc"]))
     add("swiglu_bwd", 20 * per, lambda i: ops.swiglu_bwd(S(i)["dact"], S(i)["h12"], S(i)["db"]))
     print(f"[perf {name}] B={Bn} rows/sample={T} d={d}  ({nbuf} rotating buffer sets, {per / 1e6:.1f} MB per tensor)")
+    print(f"    {'':30s} {'generation 1':>34s}   {'generation 2':>34s}")
     for tag, us, gbs in rows:
-        print(f"    {tag:30s} {us:8.1f} us  {gbs:7.0f} GB/s  {gbs / HBM_PEAK:5.2f} of HBM peak")
+        cells = [f"{u:8.1f} us {g:7.0f} GB/s {g / HBM_PEAK:5.2f} of peak" for u, g in zip(us, gbs)]
+        print(f"    {tag:30s} {cells[0]}   {cells[1]}")
 
 
 if __name__ == "__main__":
@@ -142,6 +237,10 @@ if __name__ == "__main__":
     if what in ("check", "all"):
         for shp in [(2, 256, 256), (3, 77, 1216), (2, 64, 1536), (5, 154, 768), (3, 1, 128), (64, 256, 768), (16, 1024, 1536)]:
             check(*shp)
+        for shp in [(2, 256, 256), (3, 77, 1216), (2, 64, 1536), (5, 154, 768), (3, 1, 128), (7, 33, 64),
+                    (64, 256, 768), (64, 154, 768), (16, 1024, 1536), (200, 3, 512)]:
+            check_generations(*shp)
+        ops.set_row_kernel_generation(2)
         print("ROW CHECK", "PASS" if ok_all else "FAIL")
     if what in ("perf", "all"):
         perf("cfg2 image", 64, 256, 768)

@@ -233,7 +233,11 @@ swiglu_fwd_kernel(const bf16* __restrict__ h12, bf16* __restrict__ a, long long 
 
 // da: [R, hid]; writes dh12 [R, 2*hid] and accumulates db12 [2*hid] (fp32 atomics).
 // Block = 128 threads x 8 columns = 1024 hidden columns, strip of rows_per_block rows.
-__global__ void __launch_bounds__(128)
+// 80 registers (6 blocks of 128 per SM allowed): with the default heuristics ptxas held this kernel to 60
+// registers and serialised part of the 12 loads of a trip behind the math; with the room all 12 are issued
+// first.  Measured: cfg2 text 74.0 -> 57.2 us (0.62 -> 0.81 of the HBM rate), cfg3 image 193.6 -> 165.9 us
+// (0.80 -> 0.93).  A register ping-pong over the next four rows (168 registers) was slower: 74.4 / 180.7 us.
+__global__ void __launch_bounds__(128, 6)
 swiglu_bwd_kernel(const bf16* __restrict__ da, const bf16* __restrict__ h12,
                   bf16* __restrict__ dh12, float* __restrict__ partial, long long R, int hid,
                   int rows_per_block) {
@@ -270,16 +274,23 @@ swiglu_bwd_kernel(const bf16* __restrict__ da, const bf16* __restrict__ h12,
     store8(dh12 + row * 2 * hid + hid + col, d2);
   };
   long long row = r0;
-  for (; row + 3 < r1; row += 4) {
-    uint4 ug[4], u1[4], u2[4];
+  struct Rows4 { uint4 ug[4], u1[4], u2[4]; };
+  auto load4 = [&](Rows4& t, long long rw) {
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      ug[k] = *reinterpret_cast<const uint4*>(da + (row + k) * hid + col);
-      u1[k] = *reinterpret_cast<const uint4*>(h12 + (row + k) * 2 * hid + col);
-      u2[k] = *reinterpret_cast<const uint4*>(h12 + (row + k) * 2 * hid + hid + col);
+      t.ug[k] = *reinterpret_cast<const uint4*>(da + (rw + k) * hid + col);
+      t.u1[k] = *reinterpret_cast<const uint4*>(h12 + (rw + k) * 2 * hid + col);
+      t.u2[k] = *reinterpret_cast<const uint4*>(h12 + (rw + k) * 2 * hid + hid + col);
     }
+  };
+  auto body4 = [&](const Rows4& t, long long rw) {
 #pragma unroll
-    for (int k = 0; k < 4; ++k) body(ug[k], u1[k], u2[k], row + k);
+    for (int k = 0; k < 4; ++k) body(t.ug[k], t.u1[k], t.u2[k], rw + k);
+  };
+  for (; row + 3 < r1; row += 4) {
+    Rows4 t;
+    load4(t, row);
+    body4(t, row);
   }
   for (; row < r1; ++row) {
     const uint4 ug = *reinterpret_cast<const uint4*>(da + row * hid + col);
@@ -687,8 +698,7 @@ int mmdit_swiglu_bwd(const void* da, const void* h12, void* dh12, float* db12, f
   dim3 grid((unsigned)((hidden / 8 + 127) / 128), (unsigned)nrb);
   MMDIT_CARVEOUT(swiglu_bwd_kernel);
   launch_k(swiglu_bwd_kernel, grid, dim3(128), 0, (cudaStream_t)stream, (const bf16*)da, (const bf16*)h12,
-                                                           (bf16*)dh12, db12 ? workspace : nullptr,
-                                                           rows, hidden, rpb);
+           (bf16*)dh12, db12 ? workspace : nullptr, rows, hidden, rpb);
   if (db12)
     launch_k(fold_rows_f32_kernel, dim3((2 * hidden + 255) / 256, nrb >= 32 ? 16 : 1), dim3(256), 0, (cudaStream_t)stream, 
         workspace, db12, nrb, 2 * hidden, 2 * (long long)hidden);

@@ -8,8 +8,14 @@
 //   * rows stay packed (bf16x2 words) in registers until they are used, which leaves room for the
 //     NEXT row of every warp to be in flight while the current one is computed (register ping-pong);
 //   * the elementwise math is packed fp32x2 (FADD2 / FMUL2 / FFMA2: one issue slot, two columns).
-//     Row statistics keep the first generation's sequential summation order, so y / dx are
-//     bit-identical to the first-generation kernels.
+//     Row statistics keep the first generation's sequential summation order: y, x', mean, rstd, dx and
+//     da are bit-identical to the first-generation kernels (tools/row_probe.py check, 0 differing
+//     elements at every shape); the per-sample column sums differ in the last fp32 bits because the
+//     strips are cut differently.
+// Measured (B200, graph replay over buffers larger than the L2, cfg2 image stream 16384 x 768, of the
+// 6549.8 GB/s copy rate): LN-modulate fwd 13.9 -> 9.9 us (0.55 -> 0.77), gate+residual+LN fwd 23.5 ->
+// 17.1 us (0.65 -> 0.90), gate bwd 18.9 -> 17.1 us; at d = 1536 LN bwd 57.8 -> 45.4 us, gate bwd 39.4 ->
+// 32.5 us, gate+LN fwd 107 -> 38 us (profiles/r02_row_kernels_gen2.log).
 // One warp owns one row; lane l holds columns c*256 + l*8 .. +7 of every 256-column chunk c.
 #include <stdlib.h>
 
@@ -433,8 +439,8 @@ gate_res_ln_fwd2_kernel(const bf16* __restrict__ a, const bf16* __restrict__ gat
 // ------------------------------------------------------------------ host side
 static int g_row_generation = [] {
   const char* e = getenv("MMDIT_ROW_KERNELS");
-  const int x = e ? atoi(e) : 1;   // TODO(after the GPU A/B): default 2
-  return x == 2 ? 2 : 1;
+  const int x = e ? atoi(e) : 2;
+  return x == 1 ? 1 : 2;
 }();
 int row_kernel_generation() { return g_row_generation; }
 

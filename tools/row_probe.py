@@ -37,19 +37,21 @@ def same(got, ref, tag):
 
 def close_bf16(got, ref, tag, exact):
     """second generation vs first: bit-identical where the operation order is the same (forward kernels), else
-    at most one bf16 ulp apart on at most 1 % of the elements (ptxas contracts a few mul + add pairs)"""
+    at most one bf16 ulp (plus the fp32 noise of a column sum) apart: the strips of the two generations are cut differently"""
     global ok_all
     g, r = got.float(), ref.float()
     diff = (g - r).abs()
     n = int((diff > 0).sum())
-    ulp = torch.maximum(g.abs(), r.abs()) * 2.0 ** -7 + 1e-30
+    # column sums cancel: an entry near zero carries the fp32 noise of the whole sum
+    noise = 2e-5 * float(r.abs().max()) + 1e-12
+    ulp = torch.maximum(g.abs(), r.abs()) * 2.0 ** -7 + noise
     worst = float((diff / ulp).max()) if n else 0.0
     if exact:
         bad = n != 0
     elif got.dtype == BF:
-        bad = worst > 1.001 or n > 1e-2 * got.numel()
+        bad = worst > 1.001
     else:
-        bad = float(diff.max()) > 2e-5 * float(r.abs().max()) + 1e-12
+        bad = float(diff.max()) > noise
     ok_all &= not bad
     print(f"    {tag:34s} differing: {n} of {got.numel()} (worst {worst:.2f} bf16 ulp) {'FAIL' if bad else 'ok'}")
 
@@ -94,6 +96,16 @@ def check_generations(Bn, T, d):
     g1, g2 = both_generations(gb)
     for k, nm in enumerate(("da", "dgate", "dab")):
         close_bf16(g2[k], g1[k], f"gate_bwd {nm}", nm == "da")
+
+    def sb():
+        gg = torch.Generator(device=dev).manual_seed(5)
+        h12 = torch.randn(Bn * T, 4 * d, device=dev, generator=gg).bfloat16()
+        dact = torch.randn(Bn * T, 2 * d, device=dev, generator=gg).bfloat16()
+        db = torch.zeros(4 * d, device=dev)
+        return ops.swiglu_bwd(dact, h12, db), db
+    s1, s2 = both_generations(sb)
+    close_bf16(s2[0], s1[0], "swiglu_bwd dh12", True)
+    close_bf16(s2[1], s1[1], "swiglu_bwd db12", False)   # atomics: fp32 order varies
 
     if d % 64 == 0:
         g = torch.Generator(device=dev).manual_seed(11)

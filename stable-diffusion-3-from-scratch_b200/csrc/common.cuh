@@ -64,10 +64,12 @@ int gate_residual_ln_fwd_v2(const void* a, const void* gate, const void* resid, 
                             int d, long long rows_per_batch, long long ld_gate, long long ld_mod, float eps,
                             cudaStream_t stream);
 int ln_modulate_bwd_v2(const void* dy, const void* x, const float* mean, const float* rstd, const void* scale,
-                       const void* dres, void* dx, float* workspace, long long rows, int d,
-                       long long rows_per_batch, long long ld_mod, int* bpb_out, cudaStream_t stream);
-int gate_bwd_v2(const void* dout, const void* a, const void* gate, void* da, float* workspace, long long rows,
-                int d, long long rows_per_batch, long long ld_gate, int* bpb_out, cudaStream_t stream);
+                       const void* dres, void* dx, void* dshift, void* dscale, int dmod_bf16, long long ld_dmod,
+                       float* workspace, long long rows, int d, long long rows_per_batch, long long ld_mod,
+                       int* bpb_out, cudaStream_t stream);
+int gate_bwd_v2(const void* dout, const void* a, const void* gate, void* da, void* dgate, int dgate_bf16,
+                float* dab, long long ld_dgate, long long ld_dab, float* workspace, long long rows, int d,
+                long long rows_per_batch, long long ld_gate, int* bpb_out, cudaStream_t stream);
 int qknorm_rope_fwd_v2(const void* qkv, const float* wq, const float* wk, const float* rope_cos,
                        const float* rope_sin, void* out, long long rows, int d, long long ld_in,
                        long long ld_out, int T, float eps, cudaStream_t stream);

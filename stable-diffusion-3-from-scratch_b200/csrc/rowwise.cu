@@ -565,8 +565,8 @@ int mmdit_ln_modulate_bwd(const void* dy, const void* x, const float* mean, cons
   MMDIT_REQUIRE(smem <= 48 * 1024, MMDIT_ERR_UNSUPPORTED, "ln_modulate_bwd: d=%d too wide", d);
   int bpb = 0, v2 = ROW_V2_UNSUPPORTED;
   if (row_kernel_generation() >= 2)
-    v2 = ln_modulate_bwd_v2(dy, x, mean, rstd, scale, dres, dx, workspace, rows, d, rows_per_batch, ld_mod, &bpb,
-                            (cudaStream_t)stream);
+    v2 = ln_modulate_bwd_v2(dy, x, mean, rstd, scale, dres, dx, dshift, dscale, dmod_bf16, ld_dmod, workspace, rows,
+                            d, rows_per_batch, ld_mod, &bpb, (cudaStream_t)stream);
   if (v2 == ROW_V2_UNSUPPORTED) {
     int rpb = 16;
     DISPATCH_NC(d, rpb = rows_per_block((const void*)ln_mod_bwd_kernel<NC>, smem, rows_per_batch, nb));
@@ -578,11 +578,12 @@ int mmdit_ln_modulate_bwd(const void* dy, const void* x, const float* mean, cons
   } else if (v2 != MMDIT_OK) {
     return v2;
   }
+  if (bpb == 0) return MMDIT_OK;   // the sample's strips ran as one cluster and folded their column sums
   dim3 g2((2 * d + 255) / 256, nb);
   MMDIT_CARVEOUT(fold_batch_partials_kernel);
   launch_k(fold_batch_partials_kernel, g2, dim3(256), 0, (cudaStream_t)stream, workspace, dshift, dscale, d, bpb,
                                                                   ld_dmod, ld_dmod, dmod_bf16, dmod_bf16);
-  return check_launch("ln_mod_bwd_kernel", 2);
+  return check_launch(v2 == MMDIT_OK ? "fold_batch_partials_kernel" : "ln_mod_bwd_kernel", v2 == MMDIT_OK ? 1 : 2);
 }
 
 int mmdit_gate_bwd(const void* dout, const void* a, const void* gate, void* da, void* dgate,
@@ -597,7 +598,8 @@ int mmdit_gate_bwd(const void* dout, const void* a, const void* gate, void* da, 
   MMDIT_REQUIRE(smem <= 48 * 1024, MMDIT_ERR_UNSUPPORTED, "gate_bwd: d=%d too wide", d);
   int bpb = 0, v2 = ROW_V2_UNSUPPORTED;
   if (row_kernel_generation() >= 2)
-    v2 = gate_bwd_v2(dout, a, gate, da, workspace, rows, d, rows_per_batch, ld_gate, &bpb, (cudaStream_t)stream);
+    v2 = gate_bwd_v2(dout, a, gate, da, dgate, dgate_bf16, dab, ld_dgate, ld_dab, workspace, rows, d, rows_per_batch,
+                     ld_gate, &bpb, (cudaStream_t)stream);
   if (v2 == ROW_V2_UNSUPPORTED) {
     int rpb = 16;
     DISPATCH_NC(d, rpb = rows_per_block((const void*)gate_bwd_kernel<NC>, smem, rows_per_batch, nb));
@@ -609,10 +611,11 @@ int mmdit_gate_bwd(const void* dout, const void* a, const void* gate, void* da, 
   } else if (v2 != MMDIT_OK) {
     return v2;
   }
+  if (bpb == 0) return MMDIT_OK;   // folded inside the cluster
   dim3 g2((2 * d + 255) / 256, nb);
   launch_k(fold_batch_partials_kernel, g2, dim3(256), 0, (cudaStream_t)stream, workspace, dgate, dab, d, bpb,
                                                                   ld_dgate, ld_dab, dgate_bf16, 0);
-  return check_launch("gate_bwd_kernel", 2);
+  return check_launch(v2 == MMDIT_OK ? "fold_batch_partials_kernel" : "gate_bwd_kernel", v2 == MMDIT_OK ? 1 : 2);
 }
 
 int mmdit_text_norm_fwd(const void* c, const float* w1, const float* w2, const float* sigma1,

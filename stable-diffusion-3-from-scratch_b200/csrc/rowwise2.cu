@@ -101,6 +101,60 @@ __device__ __forceinline__ void block_fold2(float* red, const float2 (&a0)[NC][4
   }
 }
 
+// Column sums of a whole sample without a second launch: the blocks of one sample are ONE thread-block
+// cluster (2..8 CTAs).  Every CTA reduces its warps in its own shared memory, the cluster synchronises,
+// and CTA r adds slice r of the 2*d columns over all CTAs through distributed shared memory
+// (ld.shared::cluster), in rank order -- the order fold_batch_partials_kernel uses over the workspace --
+// and writes the final bf16 / fp32 vectors.  No workspace traffic, no fold kernel (94 launches of ~4 us
+// per cfg2 step).  out0 / out1 as in fold_batch_partials_kernel.
+__device__ __forceinline__ float ld_dsmem_f32(uint32_t cluster_saddr) {
+  float v;
+  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(cluster_saddr));
+  return v;
+}
+template <int NC>
+__device__ __forceinline__ void cluster_fold2(float* red, const float2 (&a0)[NC][4], const float2 (&a1)[NC][4],
+                                              int d, int warp, int lane, int csize, long long b, void* out0,
+                                              void* out1, long long ld0, long long ld1, int out0_bf16,
+                                              int out1_bf16) {
+  float* mine = red + (long long)warp * 2 * d;
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    const int col = c * 256 + lane * 8;
+    if (col < d) {
+      *reinterpret_cast<float4*>(mine + col) = make_float4(a0[c][0].x, a0[c][0].y, a0[c][1].x, a0[c][1].y);
+      *reinterpret_cast<float4*>(mine + col + 4) = make_float4(a0[c][2].x, a0[c][2].y, a0[c][3].x, a0[c][3].y);
+      *reinterpret_cast<float4*>(mine + d + col) = make_float4(a1[c][0].x, a1[c][0].y, a1[c][1].x, a1[c][1].y);
+      *reinterpret_cast<float4*>(mine + d + col + 4) = make_float4(a1[c][2].x, a1[c][2].y, a1[c][3].x, a1[c][3].y);
+    }
+  }
+  __syncthreads();
+  const int n2 = 2 * d;
+  for (int i = threadIdx.x; i < n2; i += R2_THREADS) {   // in place: column i is touched by one thread only
+    float acc = 0.f;
+#pragma unroll
+    for (int w = 0; w < R2_WARPS; ++w) acc += red[(long long)w * n2 + i];
+    red[i] = acc;
+  }
+  cluster_sync_all();   // every CTA's block sums are in its shared memory and visible to the cluster
+  const int rank = (int)cluster_ctarank();
+  const int per = (n2 + csize - 1) / csize;
+  const int i1 = min(n2, (rank + 1) * per);
+  for (int i = rank * per + threadIdx.x; i < i1; i += R2_THREADS) {
+    const uint32_t local = smem_u32(red + i);
+    float acc = 0.f;
+    for (int k = 0; k < csize; ++k) acc += ld_dsmem_f32(mapa_u32(local, (uint32_t)k));
+    if (i < d) {
+      if (out0_bf16) reinterpret_cast<bf16*>(out0)[b * ld0 + i] = __float2bfloat16(acc);
+      else reinterpret_cast<float*>(out0)[b * ld0 + i] = acc;
+    } else if (out1) {
+      if (out1_bf16) reinterpret_cast<bf16*>(out1)[b * ld1 + (i - d)] = __float2bfloat16(acc);
+      else reinterpret_cast<float*>(out1)[b * ld1 + (i - d)] = acc;
+    }
+  }
+  cluster_sync_all();   // no CTA leaves while a peer may still read its shared memory
+}
+
 // Runs body(stage, row) over rows r0 + warp, r0 + warp + R2_WARPS, ... < r1 with the loads of the
 // next row issued before the current row is processed.  `load(stage, row)` fills stage 0 or 1.
 template <typename Load, typename Body>
@@ -137,7 +191,8 @@ ln_mod_bwd2_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
                    const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
                    const bf16* __restrict__ scale, const bf16* __restrict__ dres,
                    bf16* __restrict__ dx, float* __restrict__ partial, int d, long long rows_per_batch,
-                   long long ld_mod, int rows_per_block, int blocks_per_batch) {
+                   long long ld_mod, void* __restrict__ out0, void* __restrict__ out1, long long ld_out,
+                   int out_bf16, int cluster_fold, int rows_per_block, int blocks_per_batch) {
   // (no early pdl_trigger: dependents are released when this grid exits)
   pdl_wait();   // programmatic dependent launch: the previous kernel's writes are visible from here
   extern __shared__ float red[];  // (1 + scale) table during the row loop, then [R2_WARPS][2][d]
@@ -225,7 +280,11 @@ ln_mod_bwd2_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
     }
   }
   __syncthreads();   // every warp is done with the table before the fold overwrites it
-  block_fold2<NC>(red, a_sh, a_sc, partial + (long long)blockIdx.x * 2 * d, d, warp, lane);
+  if (cluster_fold)
+    cluster_fold2<NC>(red, a_sh, a_sc, d, warp, lane, blocks_per_batch, b, out0, out1, ld_out, ld_out, out_bf16,
+                      out_bf16);
+  else
+    block_fold2<NC>(red, a_sh, a_sc, partial + (long long)blockIdx.x * 2 * d, d, warp, lane);
 }
 
 // ------------------------------------------------------------------ gate bwd
@@ -239,8 +298,9 @@ template <int NC, bool FULL, bool PREFETCH>
 __global__ void __launch_bounds__(R2_THREADS, PREFETCH ? 3 : 2)
 gate_bwd2_kernel(const bf16* __restrict__ dout, const bf16* __restrict__ a,
                  const bf16* __restrict__ gate, bf16* __restrict__ da, float* __restrict__ partial,
-                 int d, long long rows_per_batch, long long ld_gate, int rows_per_block,
-                 int blocks_per_batch) {
+                 int d, long long rows_per_batch, long long ld_gate, void* __restrict__ out0,
+                 void* __restrict__ out1, long long ld0, long long ld1, int out0_bf16, int cluster_fold,
+                 int rows_per_block, int blocks_per_batch) {
   // (no early pdl_trigger: dependents are released when this grid exits)
   pdl_wait();   // programmatic dependent launch: the previous kernel's writes are visible from here
   extern __shared__ float red[];  // gate table during the row loop, then [R2_WARPS][2][d]
@@ -297,7 +357,10 @@ gate_bwd2_kernel(const bf16* __restrict__ dout, const bf16* __restrict__ a,
     }
   }
   __syncthreads();
-  block_fold2<NC>(red, a_g, a_b, partial + (long long)blockIdx.x * 2 * d, d, warp, lane);
+  if (cluster_fold)
+    cluster_fold2<NC>(red, a_g, a_b, d, warp, lane, blocks_per_batch, b, out0, out1, ld0, ld1, out0_bf16, 0);
+  else
+    block_fold2<NC>(red, a_g, a_b, partial + (long long)blockIdx.x * 2 * d, d, warp, lane);
 }
 
 // ------------------------------------------------------------ LN-modulate fwd
@@ -489,6 +552,43 @@ static void launch_strips(K kernel, size_t smem, long long rows_per_batch, int n
   launch_k(kernel, dim3((unsigned)(nb * bpb)), dim3(R2_THREADS), smem, stream, args..., rpb, bpb);
 }
 
+// MMDIT_ROW_CLUSTER=0: always the workspace + fold-kernel path
+static bool cluster_fold_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("MMDIT_ROW_CLUSTER");
+    return e ? atoi(e) != 0 : true;
+  }();
+  return on;
+}
+constexpr int MAX_FOLD_CLUSTER = 8;   // portable cluster size
+
+template <typename... KArgs>
+static bool launch_cluster(void (*kernel)(KArgs...), unsigned grid, unsigned cluster, size_t smem,
+                           cudaStream_t stream, KArgs... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(R2_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[2];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = cluster;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
+  int nclusters = 0;
+  if (cudaOccupancyMaxActiveClusters(&nclusters, kernel, &cfg) != cudaSuccess || nclusters < 1) {
+    cudaGetLastError();
+    return false;   // this cluster shape cannot be scheduled: the caller takes the workspace path
+  }
+  cudaLaunchKernelEx(&cfg, kernel, args...);   // errors surface in check_launch()
+  return true;
+}
+
 // Each returns ROW_V2_UNSUPPORTED when the shape is left to the first generation, else the launch status.
 int ln_modulate_fwd_v2(const void* x, const void* shift, const void* scale, void* y, float* mean, float* rstd,
                        long long rows, int d, long long rows_per_batch, long long ld_mod, float eps,
@@ -519,35 +619,73 @@ int gate_residual_ln_fwd_v2(const void* a, const void* gate, const void* resid, 
   return check_launch("gate_res_ln_fwd2_kernel");
 }
 
-// workspace: [nb * bpb][2][d] floats, bpb <= ceil(rows_per_batch / 8) (mmdit_rowreduce_workspace_floats)
+// workspace: [nb * bpb][2][d] floats, bpb <= ceil(rows_per_batch / 8) (mmdit_rowreduce_workspace_floats).
+// *bpb_out = partials per sample left in the workspace for fold_batch_partials_kernel, or 0 when the
+// sample's strips ran as one cluster and wrote out0 / out1 themselves.
+template <typename K, typename Tail>
+static void launch_bwd(K kernel, size_t smem, long long rows_per_batch, int nb, cudaStream_t stream, int* bpb_out,
+                       Tail&& launch_with) {
+  const int rpb = strip_rows((const void*)kernel, smem, rows_per_batch, nb, 8);
+  const int bpb = (int)((rows_per_batch + rpb - 1) / rpb);
+  if (cluster_fold_enabled() && bpb <= MAX_FOLD_CLUSTER && launch_with(true, rpb, bpb)) {
+    *bpb_out = 0;
+    return;
+  }
+  launch_with(false, rpb, bpb);
+  *bpb_out = bpb;
+}
+
 int ln_modulate_bwd_v2(const void* dy, const void* x, const float* mean, const float* rstd, const void* scale,
-                       const void* dres, void* dx, float* workspace, long long rows, int d,
-                       long long rows_per_batch, long long ld_mod, int* bpb_out, cudaStream_t stream) {
+                       const void* dres, void* dx, void* dshift, void* dscale, int dmod_bf16, long long ld_dmod,
+                       float* workspace, long long rows, int d, long long rows_per_batch, long long ld_mod,
+                       int* bpb_out, cudaStream_t stream) {
   if (ld_mod % 8 != 0) return ROW_V2_UNSUPPORTED;
   const int nb = (int)(rows / rows_per_batch);
   const int nc = (d + 255) / 256;
   size_t smem = (size_t)R2_WARPS * 2 * d * sizeof(float);
   if (smem < (size_t)nc * 256 * sizeof(float)) smem = (size_t)nc * 256 * sizeof(float);
-#define LNB(FULLV)                                                                                         \
-  launch_strips(ln_mod_bwd2_kernel<NC, FULLV, (NC <= 3)>, smem, rows_per_batch, nb, 8, stream, bpb_out,       \
-                (const bf16*)dy, (const bf16*)x, mean, rstd, (const bf16*)scale, (const bf16*)dres, (bf16*)dx, \
-                workspace, d, rows_per_batch, ld_mod)
+#define LNB(FULLV)                                                                                          \
+  launch_bwd(ln_mod_bwd2_kernel<NC, FULLV, (NC <= 3)>, smem, rows_per_batch, nb, stream, bpb_out,              \
+             [&](bool cluster, int rpb, int bpb) {                                                          \
+               auto k = ln_mod_bwd2_kernel<NC, FULLV, (NC <= 3)>;                                           \
+               if (cluster)                                                                                 \
+                 return launch_cluster(k, (unsigned)(nb * bpb), (unsigned)bpb, smem, stream, (const bf16*)dy, \
+                                       (const bf16*)x, mean, rstd, (const bf16*)scale, (const bf16*)dres,   \
+                                       (bf16*)dx, workspace, d, rows_per_batch, ld_mod, dshift, dscale,     \
+                                       ld_dmod, dmod_bf16, 1, rpb, bpb);                                    \
+               launch_k(k, dim3((unsigned)(nb * bpb)), dim3(R2_THREADS), smem, stream, (const bf16*)dy,     \
+                        (const bf16*)x, mean, rstd, (const bf16*)scale, (const bf16*)dres, (bf16*)dx,       \
+                        workspace, d, rows_per_batch, ld_mod, dshift, dscale, ld_dmod, dmod_bf16, 0, rpb,   \
+                        bpb);                                                                               \
+               return true;                                                                                 \
+             })
   R2_DISPATCH(d, LNB(true), LNB(false));
 #undef LNB
   return check_launch("ln_mod_bwd2_kernel");
 }
 
-int gate_bwd_v2(const void* dout, const void* a, const void* gate, void* da, float* workspace, long long rows,
-                int d, long long rows_per_batch, long long ld_gate, int* bpb_out, cudaStream_t stream) {
+int gate_bwd_v2(const void* dout, const void* a, const void* gate, void* da, void* dgate, int dgate_bf16,
+                float* dab, long long ld_dgate, long long ld_dab, float* workspace, long long rows, int d,
+                long long rows_per_batch, long long ld_gate, int* bpb_out, cudaStream_t stream) {
   if (ld_gate % 8 != 0) return ROW_V2_UNSUPPORTED;
   const int nb = (int)(rows / rows_per_batch);
   const int nc = (d + 255) / 256;
   size_t smem = (size_t)R2_WARPS * 2 * d * sizeof(float);
   if (smem < (size_t)nc * 256 * sizeof(float)) smem = (size_t)nc * 256 * sizeof(float);
-#define GB(FULLV)                                                                                    \
-  launch_strips(gate_bwd2_kernel<NC, FULLV, (NC <= 3)>, smem, rows_per_batch, nb, 8, stream, bpb_out,   \
-                (const bf16*)dout, (const bf16*)a, (const bf16*)gate, (bf16*)da, workspace, d,          \
-                rows_per_batch, ld_gate)
+#define GB(FULLV)                                                                                           \
+  launch_bwd(gate_bwd2_kernel<NC, FULLV, (NC <= 3)>, smem, rows_per_batch, nb, stream, bpb_out,                \
+             [&](bool cluster, int rpb, int bpb) {                                                          \
+               auto k = gate_bwd2_kernel<NC, FULLV, (NC <= 3)>;                                             \
+               if (cluster)                                                                                 \
+                 return launch_cluster(k, (unsigned)(nb * bpb), (unsigned)bpb, smem, stream,                \
+                                       (const bf16*)dout, (const bf16*)a, (const bf16*)gate, (bf16*)da,     \
+                                       workspace, d, rows_per_batch, ld_gate, dgate, (void*)dab, ld_dgate,  \
+                                       ld_dab, dgate_bf16, 1, rpb, bpb);                                    \
+               launch_k(k, dim3((unsigned)(nb * bpb)), dim3(R2_THREADS), smem, stream, (const bf16*)dout,   \
+                        (const bf16*)a, (const bf16*)gate, (bf16*)da, workspace, d, rows_per_batch, ld_gate, \
+                        dgate, (void*)dab, ld_dgate, ld_dab, dgate_bf16, 0, rpb, bpb);                      \
+               return true;                                                                                 \
+             })
   R2_DISPATCH(d, GB(true), GB(false));
 #undef GB
   return check_launch("gate_bwd2_kernel");

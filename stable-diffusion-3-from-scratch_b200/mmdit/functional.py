@@ -12,7 +12,7 @@ import os
 import torch
 from torch.autograd import Function
 
-from . import ops, streams
+from . import ops, streams, zeropool
 from .ops import BF16, F32
 
 
@@ -57,7 +57,7 @@ def _w3_dgrad(link, da, wb):
     if link is None:
         return ops.gemm(da, wb, b_major=1)
     hid = wb.shape[1]
-    link.db = torch.zeros(2 * hid, device=da.device, dtype=F32) if link.has_bias else None
+    link.db = zeropool.zeros(2 * hid, da.device) if link.has_bias else None
     link.dh12 = ops.gemm_swiglu_bwd(da, wb, link.h12, link.db)
     dummy = link.dh12[:, :hid]
     link.dummy_ptr = dummy.data_ptr()
@@ -318,7 +318,7 @@ class JointAttentionFn(Function):
                               (qkv_x[:, 2 * d:], qkv_c[:, 2 * d:]), (o_x, o_c), lse, (do_x, do_c),
                               None, (dqk_x[:, d:], dqk_c[:, d:]),
                               (dqkv_x[:, 2 * d:], dqkv_c[:, 2 * d:]), Bn, H, N, M, 0.125)
-        dw = torch.zeros((4, 64), device=qkv_x.device, dtype=F32)
+        dw = zeropool.zeros((4, 64), qkv_x.device)
         rope = (rope_cos, rope_sin) if rope_cos is not None else None
         ops.qknorm_rope_bwd(dqk_x, qkv_x, wq_x, wk_x, rope, dqkv_x, dw[0], dw[1], d, N, dq_acc=dq_acc, acc_off=0)
         ops.qknorm_rope_bwd(dqk_c, qkv_c, wq_c, wk_c, None, dqkv_c, dw[2], dw[3], d, M, dq_acc=dq_acc, acc_off=N)
@@ -395,7 +395,7 @@ class TimestepEmbedFn(Function):
     @staticmethod
     def backward(ctx, de):
         t, time_scale, denom = ctx.saved_tensors
-        ds = torch.zeros(1, device=de.device, dtype=F32)
+        ds = zeropool.zeros(1, de.device)
         ops.timestep_embed_bwd(de.contiguous(), t, time_scale, denom, ds)
         return None, ds, None
 
@@ -491,7 +491,7 @@ class SwiGLUHiddenFn(Function):
             dh, db = link.dh12, link.db
             link.dh12 = link.db = link.h12 = None
         else:
-            db = torch.zeros(h12.shape[1], device=da.device, dtype=F32) if has_bias else None
+            db = zeropool.zeros(h12.shape[1], da.device) if has_bias else None
             dh = ops.swiglu_bwd(da.reshape(-1, da.shape[-1]).contiguous(), h12, db)
         dx = ops.gemm(dh, wb, b_major=1).reshape(xshape)
         dw = _wgrad_gemm(dh, x2, [ctx.wparam])
@@ -522,8 +522,8 @@ class TextFrontFn(Function):
     def backward(ctx, g):
         c, rstd, w1, w2, s1, s2, n1, n2, wb1, wb2 = ctx.saved_tensors
         Bn, t1, t2, d = ctx.dims
-        dw1, dw2 = torch.zeros_like(w1), torch.zeros_like(w2)
-        ds1, ds2 = torch.zeros_like(s1), torch.zeros_like(s2)
+        dw1, dw2 = zeropool.zeros(w1.shape, w1.device), zeropool.zeros(w2.shape, w2.device)
+        ds1, ds2 = zeropool.zeros(s1.shape, s1.device), zeropool.zeros(s2.shape, s2.device)
         g1 = g[:, :t1].reshape(Bn * t1, d)
         dn1 = ops.gemm(g1, wb1, b_major=1, out_dtype=F32)
         dpw1 = ops.gemm(g1, n1, a_major=1, b_major=1, out_dtype=F32)

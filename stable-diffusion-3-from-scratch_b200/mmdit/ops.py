@@ -9,7 +9,7 @@ import ctypes as C
 
 import torch
 
-from . import _lib
+from . import _lib, zeropool
 from ._lib import (EPI_GATE_RESID, EPI_NONE, EPI_QKNORM, EPI_RESID, EPI_SILU, EPI_SWIGLU,  # noqa: F401
                    EPI_SWIGLU_BWD)
 
@@ -442,7 +442,7 @@ def cfg_euler_step(x, v, cfg_scale, dt):
 def colsum(x, out=None):
     R, n = x.shape
     if out is None:
-        out = torch.zeros(n, device=x.device, dtype=F32)
+        out = zeropool.zeros(n, x.device)
     _lib.check(_lib.lib().mmdit_colsum_bf16(_p(x), _p(out), R, n, x.stride(0), _s()),
                "mmdit_colsum_bf16")
     return out

@@ -16,7 +16,7 @@ torch.distributed collectives (NCCL / gloo) remain as the fallback exchange (`pe
 import torch
 import torch.distributed as dist
 
-from . import ops, shadow, streams
+from . import ops, shadow, streams, zeropool
 from .functional import rf_loss
 from .optim import FusedAdamW
 
@@ -325,6 +325,13 @@ class RFTrainer:
 
     # ------------------------------------------------------------------ step
     def _fwd_bwd(self, b):
+        zeropool.begin(b["x0"].device)     # one fill for the backward's small fp32 accumulators
+        try:
+            return self._fwd_bwd_body(b)
+        finally:
+            zeropool.end()
+
+    def _fwd_bwd_body(self, b):
         eps = torch.randn_like(b["x0"])                               # diff_model.py:235
         x_t = ops.rf_noise(b["x0"], eps, b["t"])                      # :238
         v = self.model(x_t, b["t"], b["c"], b["pooled"], b["null_pooled"], b["null_gemma"], b["null_bert"])

@@ -244,16 +244,27 @@ def perf(name, Bn, T, d):
         print(f"    {tag:30s} {cells[0]}   {cells[1]}")
 
 
-if __name__ == "__main__":
-    what = sys.argv[1] if len(sys.argv) > 1 else "all"
-    if what in ("check", "all"):
+def check_all():
+    """fused gate+LN forward == the two kernels, and every second-generation kernel (the cluster fold of the
+    column sums included: cluster sizes 1, 5 and 6 occur below) == its first-generation counterpart"""
+    global ok_all
+    ok_all = True
+    try:
         for shp in [(2, 256, 256), (3, 77, 1216), (2, 64, 1536), (5, 154, 768), (3, 1, 128), (64, 256, 768), (16, 1024, 1536)]:
             check(*shp)
         for shp in [(2, 256, 256), (3, 77, 1216), (2, 64, 1536), (5, 154, 768), (3, 1, 128), (7, 33, 64),
                     (64, 256, 768), (64, 154, 768), (16, 1024, 1536), (200, 3, 512)]:
             check_generations(*shp)
+    finally:
         ops.set_row_kernel_generation(2)
-        print("ROW CHECK", "PASS" if ok_all else "FAIL")
+    print("ROW CHECK", "PASS" if ok_all else "FAIL")
+    return ok_all
+
+
+if __name__ == "__main__":
+    what = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if what in ("check", "all"):
+        check_all()
     if what in ("perf", "all"):
         perf("cfg2 image", 64, 256, 768)
         perf("cfg2 text", 64, 154, 768)

@@ -6,6 +6,7 @@ returns torch tensors allocated by PyTorch's caching allocator.  No function
 here has a CPU or eager fallback.
 """
 import ctypes as C
+import os
 
 import torch
 
@@ -251,9 +252,21 @@ def attn_bwd(q, k, v, o, lse, d_o, dq, dk, dv, B, H, N, M, scale):
 
 
 # ------------------------------------------------------------- row kernels
+_row_generation = 1 if os.environ.get("MMDIT_ROW_KERNELS") == "1" else 2   # mirrors the library's initial value
+
+
 def set_row_kernel_generation(generation):
     """2 (default): csrc/rowwise2.cu + csrc/qknorm2.cu; 1: the first-generation kernels (A/B and regression knob)."""
+    global _row_generation
     _lib.check(_lib.lib().mmdit_set_row_kernel_generation(int(generation)), "mmdit_set_row_kernel_generation")
+    _row_generation = int(generation)
+
+
+def fused_gate_ln_max_columns():
+    """Widest row the one-pass gated residual + LayerNorm-modulate kernel is worth using for: the first
+    generation falls to one block per SM above 1024 columns (106 us vs 30 + 31 us at d = 1536); the second
+    runs 38 us there against 30 + 21 us for the two kernels."""
+    return 1536 if _row_generation >= 2 else 1024
 
 
 def ln_modulate_fwd(x, shift, scale, rows_per_batch, save_stats=True):

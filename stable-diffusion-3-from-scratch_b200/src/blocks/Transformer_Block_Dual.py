@@ -118,9 +118,9 @@ class Transformer_Block_Dual(nn.Module):
     def _gated_ln(self, a, lin, gate, resid, shift, scale, rows_per_batch):
         """(LN-mod(X'), X') with X' = resid + gate * lin(a): the out-projection's gated residual and the
         LayerNorm-modulate in front of the MLP share one pass over the GEMM output."""
-        # above 1024 columns the one-pass kernel holds too many registers (one 8-warp block per SM:
-        # 106 us vs 30 + 31 us for the two kernels at d = 1536, profiles/r02_experiments_not_shipped.md)
-        if not Fn.FUSED_GATE_LN or resid.shape[-1] > 1024:
+        # wider rows than the one-pass kernel is built for go through the two kernels (first generation:
+        # 1024 columns, second: 1536; ops.fused_gate_ln_max_columns)
+        if not Fn.FUSED_GATE_LN or resid.shape[-1] > ops.fused_gate_ln_max_columns():
             return modulate_keep(self._gated(a, lin, gate, resid, rows_per_batch), shift, scale)
         wb = packed_weight(lin, "w", [lin.weight])
         bb = None if lin.bias is None else lin.bias.detach()

@@ -75,6 +75,19 @@ def test_sass_is_blackwell_native():
     assert "HMMA." not in out.replace("UTCHMMA", "")  # no legacy mma.sync tensor path
 
 
+def test_second_generation_row_kernels_are_in_the_cubin():
+    """rowwise2.cu / qknorm2.cu: packed fp32x2 math (FFMA2 / FMUL2 / FADD2) and the thread-block-cluster
+    barrier of the DSMEM column fold must be in the shipped SASS, next to the first-generation kernels."""
+    out = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    if not out:
+        pytest.skip("cuobjdump unavailable")
+    for kernel in ("ln_mod_fwd2_kernel", "ln_mod_bwd2_kernel", "gate_res_ln_fwd2_kernel", "gate_bwd2_kernel",
+                   "qknorm_rope_fwd2_kernel", "qknorm_rope_bwd2_kernel", "ln_mod_bwd_kernel", "qknorm_rope_bwd_kernel"):
+        assert kernel in out, kernel
+    for mnemonic in ("FFMA2", "FMUL2", "FADD2", "UCGABAR_ARV", "UCGABAR_WAIT"):
+        assert mnemonic in out, mnemonic
+
+
 def test_argument_errors_are_reported_not_thrown():
     L = _lib.lib()
     a = _lib.GemmArgs()        # null pointers

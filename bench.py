@@ -153,7 +153,7 @@ def _row_bytes(kind):
         "ln_modulate_bwd": lambda dy, x, mean, rstd, scale, dres, *a, **k: (6.0 if dres is None else 8.0) * x.numel(),
         "gate_residual_fwd": lambda a_, *r, **k: 6.0 * a_.numel(),
         "gate_residual_ln_fwd": lambda a_, *r, **k: 8.0 * a_.numel(),      # read a, resid; write x', LN-mod(x')
-        "gate_bwd": lambda dout, *r, **k: 8.0 * dout.numel(),
+        "gate_bwd": lambda dout, *r, **k: 6.0 * dout.numel(),              # read dout, a; write da (lines before round 2's last pass used 8)
         "qknorm_rope_fwd": lambda qkv, wq, wk, rope, d, *r, **k: 8.0 * qkv.shape[0] * d,
         "qknorm_rope_bwd": lambda dqk, qkv, wq, wk, rope, dqkv, dwq, dwk, d, *r, **k: 14.0 * qkv.shape[0] * d,   # dq fp32 4 + dk 2 + q,k 4 + dq,dk out 4
         "swiglu_bwd": lambda da, h12, *r, **k: 5.0 * h12.numel(),      # bf16: read da (h) + h12 (2h), write dh12 (2h)

@@ -119,3 +119,40 @@ def test_synthetic_text_encoder_stub_shapes():
     h2, _ = m.text_encoders.text_to_embedding("a photo of a cat")
     assert torch.equal(h, h2)
     assert m.text_encoders.VAE.config.latent_channels == 16
+
+
+def test_fused_gate_ln_width_limit_follows_the_row_kernel_generation(monkeypatch):
+    """Host logic of the one-pass gated residual + LayerNorm-modulate (Transformer_Block_Dual.py:64-72):
+    rows up to 1536 columns take it with the second-generation kernels, up to 1024 with the first; wider
+    rows go through the two kernels."""
+    import types
+
+    import torch
+    from mmdit import ops
+    from src.blocks import Transformer_Block_Dual as T
+
+    monkeypatch.setattr(ops, "_row_generation", 2)
+    assert ops.fused_gate_ln_max_columns() == 1536
+    monkeypatch.setattr(ops, "_row_generation", 1)
+    assert ops.fused_gate_ln_max_columns() == 1024
+
+    taken = []
+
+    class FusedFn:
+        @staticmethod
+        def apply(a, wb, bb, gate, resid2, shift, scale, rpb, w, b):
+            taken.append("fused")
+            return resid2, resid2
+
+    monkeypatch.setattr(T, "GatedLinearLNFn", FusedFn)
+    monkeypatch.setattr(T, "packed_weight", lambda lin, tag, ws: ws[0])
+    monkeypatch.setattr(T, "modulate_keep", lambda x, shift, scale: (taken.append("two kernels"), (x, x))[1])
+    monkeypatch.setattr(T.Fn, "FUSED_GATE_LN", True)
+    fake = types.SimpleNamespace(_gated=lambda a, lin, gate, resid, rpb: resid)
+    for gen, width, want in ((2, 1536, "fused"), (1, 1536, "two kernels"), (1, 1024, "fused"), (2, 1792, "two kernels")):
+        monkeypatch.setattr(ops, "_row_generation", gen)
+        taken.clear()
+        lin = types.SimpleNamespace(weight=torch.zeros(1), bias=None)
+        resid = torch.zeros(2, 3, width)
+        T.Transformer_Block_Dual._gated_ln(fake, resid, lin, None, resid, None, None, 3)
+        assert taken == [want], (gen, width, taken)
